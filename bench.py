@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the GGUF mmq hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--detail]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): decode GEMV HBM GB/s over packed weight bytes.  Workload at every N:
+BASELINE configs[1], the Llama-3-8B lm_head shape — Q4_K weights [O=128256, K=4096] (295.5 MB packed,
+larger than the 126 MB L2, so every step streams them from HBM) times T=1 fp16 activations.
+A step = one pass of the hot path over one batch of synthetic activations:
+  N = 1  one `mmq_q4_k` call
+  N > 1  the layer is N-split (each rank holds O/N packed rows): broadcast X from rank 0, per-rank
+         mmq on the shard, NCCL all-gather of the [T, O/N] slices  -> "scaling": "strong"
+`value` = packed bytes of the whole layer / step time (device-timed, inputs resident in HBM, max over
+ranks).  `e2e` = the same through the reference-named Python entry point with HOST activations and a
+HOST result (pinned H2D of X and D2H of C inside the timed region; the packed weights are the layer's
+resident state, as in the reference's own usage).  `--impl reference` times the reference's CPU path
+(the oracle port of kernels/cpu_impls, all host threads) on bounded row samples of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "gguf-triton-kernel_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+FMT, O, K, T = "q4_k", 128256, 4096, 1
+WORKLOAD = "Q4_K decode GEMV, Llama-3-8B lm_head (K=4096, O=128256), T=1 [BASELINE configs[1]]"
+METRIC = "decode GEMV HBM GB/s over packed weight bytes (Q4_K, T=1)"
+L2_NOTE = "inputs larger than L2: 295.5 MB of packed weights streamed per step vs 126 MB L2"
+BLK = {"q8_0": (32, 34), "q4_k": (256, 144), "q6_k": (256, 210)}
+
+
+def packed_bytes(fmt, rows, k):
+    qk, blk = BLK[fmt]
+    return rows * (k // qk) * blk
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        return float(m["hbm_gbs"]), float(m.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic packed weights, generated on the device (every byte pattern with finite scales is valid)
+# ---------------------------------------------------------------------------------------------
+def gen_weights(torch, fmt, rows, k, device, seed):
+    qk, blk = BLK[fmt]
+    nb = rows * (k // qk)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    raw = torch.randint(0, 256, (nb, blk), dtype=torch.uint8, device=device, generator=g)
+
+    def scales(mag):
+        v = (torch.rand(nb, device=device, generator=g) * 0.75 + 0.25) * mag
+        return v.to(torch.float16).view(torch.uint8).reshape(nb, 2)
+
+    if fmt == "q8_0":
+        raw[:, 0:2] = scales(0.02)
+    elif fmt == "q4_k":
+        raw[:, 0:2] = scales(0.02 / 16)
+        raw[:, 2:4] = scales(0.02 / 16)
+    else:
+        raw[:, 208:210] = scales(0.02 / 64)
+    return raw.reshape(-1).view(torch.int8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of kernels/cpu_impls on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_path_gbs(rows_per_step, steps, warmup, threads):
+    """Times the reference's CPU path (Q8_1-quantized activations, integer block dots, fp16 accumulate —
+    kernels/cpu_impls/mmq_q4_k_q8_1_cpu.py:61-119, restated in oracle/ggq_oracle.py) on `rows_per_step`
+    rows of the workload per step, rows spread over `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import ggq_oracle as orc
+    rows_per_step = max(threads, rows_per_step // threads * threads)
+    per = rows_per_step // threads
+    A = [orc.random_blocks(FMT, per, K, seed=100 + i) for i in range(threads)]
+    X = np.random.default_rng(0).standard_normal((T, K)).astype(np.float16)
+
+    def step():
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda a: orc.mmq_cpu(FMT, a, X, per, T, K), A))
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return packed_bytes(FMT, rows_per_step, K) / dt / 1e9, dt, rows_per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = 1024 * threads  # ~0.1 s of CPU work per step: any --steps/--warmup ends within minutes
+    gbs, dt, rows = cpu_path_gbs(rows, args.steps, args.warmup, threads)
+    sample = f"{rows} of {O} rows per step (rows are independent), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * O / rows, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int8 block dots + fp16 accumulate (reference CPU arithmetic)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def timed(torch, dist, fn, steps, warmup, world):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def detail_table(torch, ext, hbm_peak):
+    """Secondary numbers (not the headline): decode GB/s per quant type / shape / T with rotating
+    weight copies > 2x L2, so each launch reads its weights from HBM."""
+    rows = []
+    shapes = [("q8_0", 4096, 4096), ("q4_k", 4096, 4096), ("q4_k", 14336, 4096), ("q4_k", 128256, 4096),
+              ("q6_k", 4096, 14336), ("q6_k", 128256, 4096), ("q8_0", 28672, 8192)]
+    for fmt, o, k in shapes:
+        nbytes = packed_bytes(fmt, o, k)
+        copies = max(1, min(64, -(-2 * 126_000_000 // nbytes)))
+        Ws = [gen_weights(torch, fmt, o, k, "cuda", 7 + i) for i in range(copies)]
+        for t in (1, 4, 8, 16):
+            X = torch.randn((t, k), device="cuda", dtype=torch.float16)
+            C = torch.empty((t, o), device="cuda", dtype=torch.float16)
+            it = [0]
+
+            def fn():
+                ext.mm(ext.FMT_ID[fmt], Ws[it[0] % copies], X, o, t, k, out=C)
+                it[0] += 1
+
+            n = max(20, copies * 3)
+            ms = timed(torch, None, fn, n, 5, 1)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            rows.append({"fmt": fmt, "O": o, "K": k, "T": t, "us": round(ms * 1e3, 2), "GBps": round(gbs, 1),
+                         "frac_measured_peak": round(gbs / hbm_peak, 3), "frac_8TBps": round(gbs / 8000.0, 3)})
+        del Ws
+        torch.cuda.empty_cache()
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from kernels import _ext as ext
+    from kernels.mmq_q4_k import mmq_q4_k
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    ext.lib()
+    hbm_peak, _, peak_src = peaks()
+
+    rows = O // world
+    assert rows * world == O
+    W = gen_weights(torch, FMT, rows, K, "cuda", 1234 + rank)
+    total_bytes = packed_bytes(FMT, O, K)
+    x_host = torch.randn((T, K), dtype=torch.float16).pin_memory()
+    x_dev = x_host.to("cuda")
+    c_shard = torch.empty((T, rows), device="cuda", dtype=torch.float16)
+    c_full = torch.empty((world, T, rows), device="cuda", dtype=torch.float16) if world > 1 else None
+    c_host = torch.empty((T, O), dtype=torch.float16).pin_memory()
+
+    # sanity: Tier-1 parity on sampled rows before anything is timed (oracle = checker only)
+    if rank == 0:
+        from oracle import ggq_oracle as orc
+        mmq_q4_k(W, x_dev, rows, T, K)
+        C = mmq_q4_k(W, x_dev, rows, T, K)
+        torch.cuda.synchronize()
+        pick = np.random.default_rng(0).choice(rows, 128, replace=False)
+        rb = packed_bytes(FMT, 1, K)
+        Wc = W.view(-1, rb)[torch.from_numpy(pick).to("cuda")].cpu().numpy().reshape(-1)
+        ref = orc.ref32(FMT, Wc, x_host.numpy(), len(pick), T, K)
+        mx, fro = orc.tier1_errors(C[:, torch.from_numpy(pick).to("cuda")].float().cpu().numpy(), ref)
+        assert mx <= orc.TIER1_MAX and fro <= orc.TIER1_FRO, ("bench parity", mx, fro)
+        parity = {"max_over_max": mx, "rel_fro": fro, "rows_sampled": len(pick)}
+
+    def step_device():
+        if world > 1:
+            dist.broadcast(x_dev, src=0)
+        ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard)
+        if world > 1:
+            dist.all_gather_into_tensor(c_full, c_shard)
+
+    def step_e2e():
+        x_dev.copy_(x_host, non_blocking=True)
+        if world > 1:
+            dist.broadcast(x_dev, src=0)
+        c = mmq_q4_k(W, x_dev, rows, T, K)
+        if world > 1:
+            dist.all_gather_into_tensor(c_full, c)
+            c_host.view(T, world, rows).copy_(c_full.permute(1, 0, 2), non_blocking=True)
+        else:
+            c_host.copy_(c, non_blocking=True)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ext.launch_count()
+    ms = timed(torch, dist, step_device, args.steps, args.warmup, world)
+    launches = (ext.launch_count() - l0) - args.warmup  # launches inside the timed region, this rank
+    ms_e2e = timed(torch, dist, step_e2e, args.steps, args.warmup, world)
+    # kernel alone (no collectives), for the roofline of the dominant kernel
+    ms_k = timed(torch, dist, lambda: ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard), args.steps, args.warmup, world)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = total_bytes / (ms * 1e-3) / 1e9
+    e2e = total_bytes / (ms_e2e * 1e-3) / 1e9
+    k_bytes = packed_bytes(FMT, rows, K)
+    achieved = k_bytes / (ms_k * 1e-3) / 1e9
+    cpu_threads = 1
+    cpu_gbs, cpu_dt, cpu_rows = cpu_path_gbs(65536, 1, 0, cpu_threads)
+    out = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 (fp16 activations x in-register dequantized weights, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": L2_NOTE, "parallelism": f"N-split x{world}" if world > 1 else "single GPU",
+                   "fmt": FMT, "O": O, "K": K, "T": T},
+        "e2e": {"value": e2e, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": T * K * 2,
+                "d2h_bytes_per_step": T * O * 2},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "ggq::dec::decode_kernel<Q4_K,NT=1,AT=1>", "achieved": achieved,
+                     "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "frac_of_8TBps_nominal": achieved / 8000.0, "us_per_launch": ms_k * 1e3,
+                     "algorithmic_bytes_per_launch": k_bytes, "traffic": None},
+        "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
+                         "sample": f"{cpu_rows} of {O} rows, one pass ({cpu_dt:.1f} s), numpy oracle port of kernels/cpu_impls"},
+        "parity": parity,
+    }
+    if args.detail:
+        out["detail"] = detail_table(torch, ext, hbm_peak)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--detail", action="store_true", help="also sweep quant types / shapes / T (secondary table)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

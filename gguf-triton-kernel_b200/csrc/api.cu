@@ -1,0 +1,167 @@
+// api.cu — the extern "C" boundary of libggq.so (include/ggq.h): validation + family dispatch.
+#include <atomic>
+
+#include "../../include/ggq.h"
+#include "common.cuh"
+#include "formats.cuh"
+
+namespace ggq {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+static int validate(int fmt, const void* W, const void* X, void* const* C_out, int n_out, int64_t ldx, int64_t ldc,
+                    int64_t O, int64_t T, int64_t K) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 0 || T < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    if (n_out < 1 || n_out > 8 || ldx < K || ldc < O) return GGQ_E_SHAPE;
+    if (O > (int64_t{1} << 31) || T > (int64_t{1} << 24) || K > (int64_t{1} << 24)) return GGQ_E_SHAPE;
+    if (O == 0 || T == 0) return 0;
+    if (!C_out) return GGQ_E_POINTER;
+    for (int i = 0; i < n_out; ++i)
+        if (!C_out[i]) return GGQ_E_POINTER;
+    if (K > 0 && (!W || !X)) return GGQ_E_POINTER;
+    return 0;
+}
+
+static int select_family(int fmt, const MmArgs& a) {
+    if (a.T <= 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;
+    if (a.T >= 64 && prefill_supports(fmt, a)) return GGQ_FAMILY_PREFILL;
+    if (a.T > 16 && a.T < 64 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;  // looped over 16-token groups
+    return GGQ_FAMILY_GENERIC;
+}
+
+// K == 0: the product is an all-zero [T, O]; written by a tiny kernel so the call stays asynchronous.
+__global__ void zero_out_kernel(OutPtrs outs, int64_t ldc, int64_t O, int64_t T) {
+    const int64_t n = O * T;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = i / O, o = i % O;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < outs.n) outs.p[j][t * ldc + o] = __float2half_rn(0.f);
+    }
+}
+
+static int mm(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc, int64_t O,
+              int64_t T, int64_t K, int family, void* stream) {
+    const int v = validate(fmt, W, X, C_out, n_out, ldx, ldc, O, T, K);
+    if (v != 0) return v;
+    if (O == 0 || T == 0) return 0;
+    MmArgs a{};
+    a.W = static_cast<const uint8_t*>(W);
+    a.X = X;
+    for (int i = 0; i < n_out; ++i) a.C[i] = C_out[i];
+    a.n_out = n_out;
+    a.ldx = ldx;
+    a.ldc = ldc;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    a.stream = static_cast<cudaStream_t>(stream);
+    if (K == 0) {
+        zero_out_kernel<<<64, 256, 0, a.stream>>>(make_outs(a), ldc, O, T);
+        count_launch();
+        return static_cast<int>(cudaGetLastError());
+    }
+    if (family == GGQ_FAMILY_AUTO) family = select_family(fmt, a);
+    switch (family) {
+        case GGQ_FAMILY_GENERIC: return launch_generic(fmt, a);
+        case GGQ_FAMILY_DECODE: return decode_supports(fmt, a) ? launch_decode(fmt, a) : GGQ_E_FAMILY;
+        case GGQ_FAMILY_PREFILL: return prefill_supports(fmt, a) ? launch_prefill(fmt, a) : GGQ_E_FAMILY;
+    }
+    return GGQ_E_FAMILY;
+}
+
+static int dequant(int fmt, const void* W, void* out, int64_t O, int64_t K, void* stream) {
+    if (O < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    if (O == 0 || K == 0) return 0;
+    if (!W || !out) return GGQ_E_POINTER;
+    return launch_dequant(fmt, static_cast<const uint8_t*>(W), out, O, K, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace ggq
+
+using namespace ggq;
+
+extern "C" {
+
+int ggq_mm_q8_0_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream) {
+    void* outs[1] = {C};
+    return mm(GGQ_Q8_0, W, X, K, outs, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);
+}
+int ggq_mm_q4_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream) {
+    void* outs[1] = {C};
+    return mm(GGQ_Q4_K, W, X, K, outs, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);
+}
+int ggq_mm_q6_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream) {
+    void* outs[1] = {C};
+    return mm(GGQ_Q6_K, W, X, K, outs, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);
+}
+
+int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc, int64_t O,
+              int64_t T, int64_t K, int family, void* stream) {
+    if (family < GGQ_FAMILY_AUTO || family > GGQ_FAMILY_PREFILL) return GGQ_E_FAMILY;
+    return mm(fmt, W, X, ldx, C_out, n_out, ldc, O, T, K, family, stream);
+}
+
+int ggq_dequant_q8_0_f16(const void* W, void* out, int64_t O, int64_t K, void* stream) {
+    return dequant(GGQ_Q8_0, W, out, O, K, stream);
+}
+int ggq_dequant_q4_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream) {
+    return dequant(GGQ_Q4_K, W, out, O, K, stream);
+}
+int ggq_dequant_q6_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream) {
+    return dequant(GGQ_Q6_K, W, out, O, K, stream);
+}
+
+int64_t ggq_packed_nbytes(int fmt, int64_t O, int64_t K) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    return O * (K / fmt_qk(fmt)) * fmt_blk(fmt);
+}
+
+int ggq_select_family(int fmt, int64_t O, int64_t T, int64_t K) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 0 || T < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    MmArgs a{};
+    a.W = reinterpret_cast<const uint8_t*>(uintptr_t{256});  // alignment-neutral placeholder
+    a.X = reinterpret_cast<const void*>(uintptr_t{256});
+    a.n_out = 1;
+    a.ldx = K;
+    a.ldc = O;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    return select_family(fmt, a);
+}
+
+int64_t ggq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* ggq_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case GGQ_E_SHAPE: return "ggq: invalid shape (K must be a multiple of the block size; sizes/strides in range)";
+        case GGQ_E_POINTER: return "ggq: null data pointer";
+        case GGQ_E_FAMILY: return "ggq: requested kernel family does not support this shape";
+        case GGQ_E_FORMAT: return "ggq: unknown quant format";
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "ggq: unknown error";
+}
+
+int ggq_version(void) { return GGQ_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// common.cuh — host-side helpers shared by the translation units of libggq.so.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ggq {
+
+struct MmArgs {
+    const uint8_t* W;     // packed weight rows
+    const void* X;        // fp16 [T, ldx]
+    void* C[8];           // fp16 outputs, each [T, ldc]
+    int n_out;
+    int64_t ldx, ldc;
+    int64_t O, T, K;
+    cudaStream_t stream;
+};
+
+// Output pointers passed to kernels by value.  n > 1 = the same tile is also stored to peer-mapped
+// buffers of other ranks (fused N-split all-gather).
+struct OutPtrs {
+    __half* p[8];
+    int n;
+};
+inline OutPtrs make_outs(const MmArgs& a) {
+    OutPtrs o;
+    for (int i = 0; i < 8; ++i) o.p[i] = static_cast<__half*>(a.C[i < a.n_out ? i : 0]);
+    o.n = a.n_out;
+    return o;
+}
+
+void count_launch(int n = 1);
+int num_sms();  // SM count of the current device (cached per device)
+
+// families (one launcher per translation unit); return cudaError_t / GGQ_E_*
+int launch_generic(int fmt, const MmArgs& a);
+int launch_decode(int fmt, const MmArgs& a);
+int launch_prefill(int fmt, const MmArgs& a);
+bool decode_supports(int fmt, const MmArgs& a);
+bool prefill_supports(int fmt, const MmArgs& a);
+
+int launch_dequant(int fmt, const uint8_t* W, void* out, int64_t O, int64_t K, cudaStream_t s);
+
+}  // namespace ggq

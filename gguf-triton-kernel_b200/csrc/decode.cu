@@ -1,0 +1,385 @@
+// decode.cu — HBM-bound skinny GEMM (T <= 16 tokens per pass): C[T, O] = X[T, K] . dequant(W)[O, K]^T
+//
+// Persistent kernel, one CTA per SM, NW consumer warps, no dedicated producer: every warp runs its
+// OWN ring of TMA bulk copies (cp.async.bulk + mbarrier complete_tx) over the packed bytes of the
+// 16-row tiles it owns, so there is no cross-warp synchronisation on the weight stream at all:
+//
+//     for each of my (tile, k-chunk) items:   wait(full[stage]) -> prep scales -> 16x{8,16} MMA tile
+//                                             -> re-arm the stage with the item STAGES ahead
+//
+// A stage holds CHUNK_BLOCKS blocks of each of the tile's 16 rows (16 bulk copies of 420..576 B,
+// issued by 16 lanes); rows are copied verbatim, 16-byte aligned supersets where a chunk starts
+// mid-vector (Q6_K).  Activations are staged once per K-slice as raw fp16 rows, also by bulk copy,
+// plus a table of per-block activation sums that cancels the integer->fp16 bias (decode_tile.cuh).
+//
+// Work decomposition (all static, chosen on the host):
+//   KW  warps cooperating on one tile (split over K chunks, reduced through shared memory) — 1 when
+//       there are at least as many tiles as warps on the GPU, up to 8 for small O
+//   AT  tiles whose accumulators a warp keeps live while the CTA walks the K-slices (4 when the
+//       activations of all tokens do not fit in shared memory at once, else 1)
+// HBM traffic = packed weight bytes once (+ <= 3 % activations/outputs); roofline: HBM bandwidth.
+#include <algorithm>
+
+#include "../../include/ggq.h"
+#include "common.cuh"
+#include "decode_tile.cuh"
+#include "formats.cuh"
+#include "ptx.cuh"
+
+namespace ggq {
+namespace dec {
+
+constexpr int NW = 8;                     // warps per CTA
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+
+struct Params {
+    const uint8_t* W;
+    const uint8_t* X;
+    OutPtrs outs;
+    int64_t ldx_bytes, ldc, O, rowB;
+    int T, K, nb;
+    int num_tiles;     // ceil(O / 16)
+    int KW;            // warps per tile
+    int nc;            // chunks per row
+    int cps;           // chunks per K-slice
+    int n_slices;
+    int num_batches;
+    int stages;
+    uint32_t x_stride;  // bytes between token rows in shared memory
+    uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red;
+};
+
+template <int FMT, int NT, int AT>
+__global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
+    using G = Geo<FMT>;
+    constexpr int STAGE_BYTES = 16 * G::SLOT;
+    constexpr int SCR_BYTES = 16 * G::CHUNK_BLOCKS * G::SCRATCH_PER_BLOCK;
+    constexpr int TPAD = 8 * NT;
+    extern __shared__ __align__(128) uint8_t smem[];
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const Lane L{lane, lane >> 2, lane & 3};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);  // [0]: activations, [1 + w*stages + s]: ring
+    uint8_t* xs = smem + p.off_x;
+    float* tbl = reinterpret_cast<float*>(smem + p.off_tbl);
+    const int STG = p.stages;
+    uint8_t* ring = smem + p.off_ring + static_cast<size_t>(w) * STG * STAGE_BYTES;
+    uint8_t* scr = smem + p.off_scr + static_cast<size_t>(w) * SCR_BYTES;
+    float* red = reinterpret_cast<float*>(smem + p.off_red);
+    uint64_t* my_full = bars + 1 + w * STG;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
+    auto tile_of = [&](int batch, int a) -> int64_t {
+        return (static_cast<int64_t>(batch) * gridDim.x + blockIdx.x) * (WT * AT) + tg * AT + a;
+    };
+    auto slice_chunks = [&](int slice) { return min(p.cps, p.nc - slice * p.cps); };
+
+    // ---- producer cursor: walks exactly the item sequence the consumer loops below walk ----------
+    struct Cur {
+        int batch, slice, a, ci;
+        bool done;
+    };
+    auto normalize = [&](Cur& c) {
+        while (true) {
+            if (c.batch >= p.num_batches) { c.done = true; return; }
+            if (c.slice >= p.n_slices) { c.slice = 0; c.a = 0; c.ci = sub; ++c.batch; continue; }
+            if (c.a >= AT) { c.a = 0; c.ci = sub; ++c.slice; continue; }
+            if (tile_of(c.batch, c.a) >= p.num_tiles || c.ci >= slice_chunks(c.slice)) { ++c.a; c.ci = sub; continue; }
+            return;
+        }
+    };
+    auto issue = [&](const Cur& c, int stage) {
+        const int64_t row0 = tile_of(c.batch, c.a) * 16;
+        const int chunk = c.slice * p.cps + c.ci;
+        const int b0 = chunk * G::CHUNK_BLOCKS;
+        const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
+        const int goff = b0 * G::BLK;
+        const int src = goff & ~15;
+        const int len = ((goff + nblk * G::BLK + 15) & ~15) - src;
+        const int64_t left = p.O - row0;
+        const int nrows = left < 16 ? static_cast<int>(left) : 16;
+        uint64_t* bar = my_full + stage;
+        if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(len * nrows));
+        __syncwarp();
+        if (lane < nrows)
+            bulk_g2s(ring + stage * STAGE_BYTES + lane * G::SLOT, p.W + (row0 + lane) * p.rowB + src,
+                     static_cast<uint32_t>(len), bar);
+    };
+
+    Cur pc{0, 0, 0, sub, false};
+    normalize(pc);
+    for (int s = 0; s < STG && !pc.done; ++s) {
+        issue(pc, s);
+        pc.ci += KW;
+        normalize(pc);
+    }
+
+    uint32_t full_phase = 0, x_phase = 0;
+    int cstage = 0;
+    const int tok0 = min(L.g, p.T - 1), tok1 = min(8 + L.g, p.T - 1);
+
+    for (int batch = 0; batch < p.num_batches; ++batch) {
+        Acc<NT> acc[AT];
+#pragma unroll
+        for (int a = 0; a < AT; ++a)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[a].v[nt][i] = 0.f;
+
+        for (int slice = 0; slice < p.n_slices; ++slice) {
+            const int nsc = slice_chunks(slice);
+            if (p.n_slices > 1 || batch == 0) {
+                // ---- stage this K-slice of the activations + its block-sum table ----------------
+                const int e0 = slice * p.cps * G::CHUNK_ELEMS;
+                const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
+                __syncthreads();  // every warp is done with the previous slice's x / tbl
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
+                    for (int t = 0; t < p.T; ++t)
+                        bulk_g2s(xs + t * p.x_stride, p.X + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
+                                 static_cast<uint32_t>(ne * 2), &bars[0]);
+                }
+                mbar_wait(&bars[0], x_phase);
+                x_phase ^= 1;
+                const int ngrp = ne / G::GROUP;
+                for (int idx = tid; idx < ngrp * TPAD; idx += NW * 32) {
+                    const int j = idx / TPAD, col = idx % TPAD;
+                    float sum = 0.f;
+                    if (col < p.T) {
+                        const uint4* src = reinterpret_cast<const uint4*>(xs + col * p.x_stride + j * G::GROUP * 2);
+#pragma unroll
+                        for (int v = 0; v < G::GROUP / 8; ++v) {
+                            const uint4 q = src[v];
+                            const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                sum += h2f(r[h] & 0xffffu);
+                                sum += h2f(r[h] >> 16);
+                            }
+                        }
+                    }
+                    tbl[idx] = sum * G::TBL_MUL;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                if (tile_of(batch, a) >= p.num_tiles) continue;  // warp-uniform
+                for (int ci = sub; ci < nsc; ci += KW) {
+                    mbar_wait(my_full + cstage, (full_phase >> cstage) & 1u);
+                    full_phase ^= 1u << cstage;
+                    const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
+                    StageArgs s;
+                    s.rows = ring + cstage * STAGE_BYTES;
+                    s.data_off = (b0 * G::BLK) & 15;
+                    s.nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
+                    s.xrow[0] = xs + tok0 * p.x_stride;
+                    s.xrow[1] = xs + tok1 * p.x_stride;
+                    s.k0 = ci * G::CHUNK_ELEMS;
+                    s.tbl = tbl;
+                    s.tpad = TPAD;
+                    s.scratch = scr;
+                    Tile<FMT, NT>::prep(L, s);
+                    __syncwarp();
+                    Tile<FMT, NT>::compute(L, s, acc[a]);
+                    __syncwarp();  // all lanes are done reading the stage and the scratch
+                    if (!pc.done) {
+                        issue(pc, cstage);
+                        pc.ci += KW;
+                        normalize(pc);
+                    }
+                    cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+                }
+            }
+        }
+
+        // ---- epilogue: (reduce over the KW warps of a tile,) round to fp16, store -----------------
+        if (KW > 1) {
+            __syncthreads();  // previous batch's readers of `red` are done
+#pragma unroll
+            for (int a = 0; a < AT; ++a)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        red[(((w * AT + a) * NT + nt) * 4 + i) * 32 + lane] = acc[a].v[nt][i];
+            __syncthreads();
+            if (sub == 0) {
+#pragma unroll
+                for (int a = 0; a < AT; ++a)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float v = acc[a].v[nt][i];
+                            for (int k = 1; k < KW; ++k) v += red[((((w + k) * AT + a) * NT + nt) * 4 + i) * 32 + lane];
+                            acc[a].v[nt][i] = v;
+                        }
+            }
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                const int64_t tile = tile_of(batch, a);
+                if (tile >= p.num_tiles) continue;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t row = tile * 16 + L.g + ((i & 2) ? 8 : 0);
+                        const int col = 8 * nt + 2 * L.t + (i & 1);
+                        if (row < p.O && col < p.T) {
+                            const __half h = __float2half_rn(acc[a].v[nt][i]);
+#pragma unroll
+                            for (int o = 0; o < 8; ++o)
+                                if (o < p.outs.n) p.outs.p[o][col * p.ldc + row] = h;
+                        }
+                    }
+            }
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct Plan {
+    Params p;
+    int nt, at, grid;
+    size_t smem;
+};
+
+template <int FMT>
+static bool make_plan(const MmArgs& a, int T, Plan& pl) {
+    using G = Geo<FMT>;
+    Params& p = pl.p;
+    p = Params{};
+    p.W = a.W;
+    p.X = static_cast<const uint8_t*>(a.X);
+    p.outs = make_outs(a);
+    p.ldx_bytes = a.ldx * 2;
+    p.ldc = a.ldc;
+    p.O = a.O;
+    p.T = T;
+    p.K = static_cast<int>(a.K);
+    p.nb = static_cast<int>(a.K / G::QK);
+    p.rowB = static_cast<int64_t>(p.nb) * G::BLK;
+    p.num_tiles = static_cast<int>((a.O + 15) / 16);
+    p.nc = (p.nb + G::CHUNK_BLOCKS - 1) / G::CHUNK_BLOCKS;
+    pl.nt = T > 8 ? 2 : 1;
+    const int tpad = 8 * pl.nt;
+    const int sms = num_sms();
+
+    int kw = 1;
+    while (kw < NW && static_cast<int64_t>(p.num_tiles) * kw < static_cast<int64_t>(sms) * NW && kw * 2 <= p.nc) kw *= 2;
+    p.KW = kw;
+    const int wt = NW / kw;
+
+    constexpr int STAGE_BYTES = 16 * G::SLOT;
+    constexpr int SCR_BYTES = 16 * G::CHUNK_BLOCKS * G::SCRATCH_PER_BLOCK;
+    const uint32_t xpad = (FMT == 1) ? 64u : 32u;  // x row pitch = 64 (128-bit loads) / 32 (64-bit loads) mod 128
+    auto layout = [&](int cps, int stages, int at, bool commit) -> size_t {
+        const size_t elems = static_cast<size_t>(cps) * G::CHUNK_ELEMS;
+        const uint32_t xstride = static_cast<uint32_t>(elems * 2 + xpad);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 127) & ~size_t{127}; return o; };
+        const size_t o_bars = take(8 * (1 + NW * MAX_STAGES));
+        const size_t o_x = take(static_cast<size_t>(T) * xstride);
+        const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
+        const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
+        const size_t o_scr = take(static_cast<size_t>(NW) * SCR_BYTES);
+        const size_t o_red = take(kw > 1 ? static_cast<size_t>(NW) * at * pl.nt * 4 * 32 * 4 : 0);
+        if (commit) {
+            p.x_stride = xstride;
+            p.off_bars = static_cast<uint32_t>(o_bars);
+            p.off_x = static_cast<uint32_t>(o_x);
+            p.off_tbl = static_cast<uint32_t>(o_tbl);
+            p.off_ring = static_cast<uint32_t>(o_ring);
+            p.off_scr = static_cast<uint32_t>(o_scr);
+            p.off_red = static_cast<uint32_t>(o_red);
+        }
+        return off;
+    };
+
+    // whole K in one slice if it fits next to a >= 2-stage ring; otherwise the largest even slicing
+    int cps = p.nc, at = 1, stages = 2;
+    if (layout(cps, 2, 1, false) > SMEM_LIMIT) {
+        at = 4;
+        int slices = 2;
+        for (;; ++slices) {
+            cps = (p.nc + slices - 1) / slices;
+            if (layout(cps, 2, at, false) <= SMEM_LIMIT) break;
+            if (cps == 1) return false;
+        }
+    }
+    while (stages < MAX_STAGES && layout(cps, stages + 1, at, false) <= SMEM_LIMIT) ++stages;
+    p.cps = cps;
+    p.n_slices = (p.nc + cps - 1) / cps;
+    p.stages = stages;
+    pl.at = at;
+    pl.smem = layout(cps, stages, at, true);
+    pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt * at - 1) / (wt * at)));
+    p.num_batches = (p.num_tiles + pl.grid * wt * at - 1) / (pl.grid * wt * at);
+    return true;
+}
+
+template <int FMT, int NT, int AT>
+static int launch_kernel(const Plan& pl, cudaStream_t stream) {
+    auto kern = decode_kernel<FMT, NT, AT>;
+    static int configured_dev_mask[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured_dev_mask[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured_dev_mask[dev] = 1;
+    }
+    kern<<<pl.grid, NW * 32, pl.smem, stream>>>(pl.p);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <int FMT>
+static int launch_fmt(const MmArgs& a) {
+    for (int64_t t0 = 0; t0 < a.T; t0 += 16) {  // T > 16: 16-token passes (weights re-read per pass)
+        MmArgs s = a;
+        s.X = static_cast<const __half*>(a.X) + t0 * a.ldx;
+        for (int i = 0; i < a.n_out; ++i) s.C[i] = static_cast<__half*>(a.C[i]) + t0 * a.ldc;
+        const int T = static_cast<int>(std::min<int64_t>(16, a.T - t0));
+        Plan pl;
+        if (!make_plan<FMT>(s, T, pl)) return GGQ_E_FAMILY;
+        int rc;
+        if (pl.nt == 1) rc = pl.at == 1 ? launch_kernel<FMT, 1, 1>(pl, a.stream) : launch_kernel<FMT, 1, 4>(pl, a.stream);
+        else rc = pl.at == 1 ? launch_kernel<FMT, 2, 1>(pl, a.stream) : launch_kernel<FMT, 2, 4>(pl, a.stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+}  // namespace dec
+
+bool decode_supports(int fmt, const MmArgs& a) {
+    if (a.T < 1 || a.O < 1 || a.K < fmt_qk(fmt)) return false;
+    if ((reinterpret_cast<uintptr_t>(a.W) & 15) || (reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx & 7)) return false;
+    const int64_t nb = a.K / fmt_qk(fmt);
+    if ((nb * fmt_blk(fmt)) & 15) return false;  // rows must be whole 16-byte vectors (Q8_0 / Q6_K: nb % 8 == 0)
+    return true;
+}
+
+int launch_decode(int fmt, const MmArgs& a) {
+    switch (fmt) {
+        case GGQ_Q8_0: return dec::launch_fmt<0>(a);
+        case GGQ_Q4_K: return dec::launch_fmt<1>(a);
+        case GGQ_Q6_K: return dec::launch_fmt<2>(a);
+    }
+    return GGQ_E_FORMAT;
+}
+
+}  // namespace ggq

@@ -1,0 +1,403 @@
+// decode_tile.cuh — lane-level code of the decode family (T <= 16 per pass).
+//
+// One warp owns a 16-row weight tile.  Packed row chunks sit in shared memory exactly as they lie in
+// HBM (TMA bulk copies, no repacking); each lane unpacks the 2x4 weights it needs for one
+// mma.sync.m16n8k16 (f16 x f16 -> f32) straight into the A fragment, the B fragment is read from the
+// raw fp16 activation rows (also TMA-staged), and block / sub-block scales are applied to the fp32
+// MMA result ("post-scaling"), so dequantized weights never exist outside registers:
+//
+//   Q8_0  A = 1152 + q  (0x6400 | (q ^ 0x80)),  D starts at -1152*sum32(x);   acc += d * D
+//   Q4_K  A = 1024 + q  (low nibbles) / 64 + q (high nibbles, 0x5400 | (q << 4));
+//         acc += (d*sc_j) * D_j - (dmin*m_j + bias_j*d*sc_j) * sum32_j(x)
+//   Q6_K  A = 1024 + q6 (0x6400 | q6),          D starts at -1056*sum16(x);   acc += (d*sc_j) * D_j
+//
+// The integer->fp16 "magic bias" costs one LOP3/PRMT per weight pair; products are exact in the
+// tensor core and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
+// agree, lane t of a quad always takes the 4 weights that share one 32-bit word and the 4 matching
+// consecutive activations.
+//
+// This header is also compiled for the host (tests/host/emu_decode.cpp) where a 32-thread warp
+// emulator supplies mma/syncwarp, so the bit manipulation is verified against the oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#define GGQ_DEV __device__ __forceinline__
+namespace ggq {
+namespace dec {
+GGQ_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+GGQ_DEV uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+GGQ_DEV float h2f(uint32_t bits) { return __half2float(__ushort_as_half(static_cast<unsigned short>(bits))); }
+// D = A(16x16, row) * B(16x8, col) + C, fp16 inputs, fp32 accumulate (HMMA.16816.F32 on sm_100a)
+GGQ_DEV void mma16816(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[4]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+}  // namespace dec
+}  // namespace ggq
+#else
+#include "../../tests/host/cuda_shim.h"
+#define GGQ_DEV inline
+#endif
+
+namespace ggq {
+namespace dec {
+
+// ---- per-format staging geometry -------------------------------------------------------------
+// CHUNK_BLOCKS blocks of one row form the unit a pipeline stage holds for each of the 16 rows.
+// SLOT is the shared-memory pitch between the 16 rows of a stage; it is >= the largest copy
+// (chunk bytes + 16-byte alignment slack) and chosen so the per-lane loads below are bank-conflict free.
+template <int FMT> struct Geo;
+template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B; lanes read 32-bit words: slot/4 % 32 == 12
+    static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = 16, CHUNK_ELEMS = 512, CHUNK_BYTES = 544, SLOT = 560;
+    static constexpr int GROUP = 32;            // activations per pre-summed group (one block)
+    static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
+    static constexpr float TBL_MUL = -1152.f;
+};
+template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B; lanes read 64-bit: slot % 128 == 96
+    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 608;
+    static constexpr int GROUP = 32;
+    static constexpr int SCRATCH_PER_BLOCK = 64;
+    static constexpr float TBL_MUL = 1.f;
+};
+template <> struct Geo<2> {  // Q6_K: 2 blocks = 512 weights = 420 B (+ up to 12 B of alignment slack)
+    static constexpr int QK = 256, BLK = 210, CHUNK_BLOCKS = 2, CHUNK_ELEMS = 512, CHUNK_BYTES = 420, SLOT = 464;
+    static constexpr int GROUP = 16;
+    static constexpr int SCRATCH_PER_BLOCK = 64;
+    static constexpr float TBL_MUL = -1056.f;
+};
+
+struct Lane {
+    int lane, g, t;  // g = lane >> 2 (row / token group), t = lane & 3 (k group)
+};
+
+// What one warp needs to consume one stage.
+struct StageArgs {
+    const uint8_t* rows;      // stage base: 16 row slots of Geo::SLOT bytes
+    int data_off;             // byte offset of the chunk inside every slot (alignment slack)
+    int nblk;                 // blocks in this chunk (<= CHUNK_BLOCKS; even for Q8_0 / Q6_K)
+    const uint8_t* xrow[2];   // per n-tile: this lane's activation row (token), at slice-relative k = 0
+    int k0;                   // slice-relative element index of the chunk's first weight
+    const float* tbl;         // [k / GROUP][TPAD] pre-summed activations times Geo::TBL_MUL
+    int tpad;                 // 8 * NT
+    uint8_t* scratch;         // this warp's prepared-scale area (SCRATCH_PER_BLOCK * 16 * CHUNK_BLOCKS)
+};
+
+GGQ_DEV uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+GGQ_DEV uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
+GGQ_DEV uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+GGQ_DEV float4 ld128f(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+GGQ_DEV float2 ld64f(const float* p) { return *reinterpret_cast<const float2*>(p); }
+GGQ_DEV uint32_t ld16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+// acc[0,1] belong to row g, acc[2,3] to row g+8 (mma C fragment order)
+template <int NT> struct Acc {
+    float v[NT][4];
+};
+
+// =============================================================================================
+// Q8_0
+// =============================================================================================
+// Two blocks = 68 B = 17 words:  [d0 q0 q1][q2..q5]...[q26..q29][q30 q31 d1][Q0..Q3]...[Q28..Q31]
+// even block: lane t takes word 1+t (q[2+4t..5+4t]) and word 5+t (q[18+4t..21+4t]); for t == 3 the
+// second word is rebuilt as [q30 q31 q0 q1] from words 8 and 0.  odd block: words 9+t and 13+t.
+GGQ_DEV void q8_to_h2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    const uint32_t u = w ^ 0x80808080u;       // q + 128 in every byte
+    lo = prmt(u, 0x64646464u, 0x5140);        // halves (0x64|u0, 0x64|u1) = 1152 + q
+    hi = prmt(u, 0x64646464u, 0x7362);
+}
+
+template <int NT>
+GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
+    using G = Geo<0>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    const uint32_t wrap_sel = (L.t == 3) ? 0x7610u : 0x3210u;
+    const int t4 = 4 * L.t;
+    for (int p = 0; p < s.nblk / 2; ++p) {
+        const uint8_t* a = r0 + 68 * p;
+        const uint8_t* b = r1 + 68 * p;
+        const uint32_t a0w = ld32(a), a8w = ld32(a + 32), b0w = ld32(b), b8w = ld32(b + 32);
+        uint32_t ae1 = ld32(a + 4 + t4), ae2 = ld32(a + 20 + t4), ao1 = ld32(a + 36 + t4), ao2 = ld32(a + 52 + t4);
+        uint32_t be1 = ld32(b + 4 + t4), be2 = ld32(b + 20 + t4), bo1 = ld32(b + 36 + t4), bo2 = ld32(b + 52 + t4);
+        ae2 = prmt(ae2, a0w, wrap_sel);
+        be2 = prmt(be2, b0w, wrap_sel);
+        const float da_e = h2f(a0w & 0xffffu), da_o = h2f(a8w >> 16);
+        const float db_e = h2f(b0w & 0xffffu), db_o = h2f(b8w >> 16);
+        const int kb = s.k0 + 64 * p;  // first weight of the even block (slice relative)
+        uint32_t fa[4], fb[4];         // A fragments of the two k16 steps of a block
+        // ---- even block: activations start at k = 2 (mod 4) -> two 32-bit loads per fragment
+        q8_to_h2(ae1, fa[0], fa[2]);
+        q8_to_h2(be1, fa[1], fa[3]);
+        q8_to_h2(ae2, fb[0], fb[2]);
+        q8_to_h2(be2, fb[1], fb[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint8_t* x = s.xrow[nt] + 2 * kb;
+            const float2 c = ld64f(s.tbl + (kb >> 5) * s.tpad + 8 * nt + 2 * L.t);
+            float d[4] = {c.x, c.y, c.x, c.y};
+            uint32_t bf[2];
+            bf[0] = ld32(x + 2 * (2 + t4));
+            bf[1] = ld32(x + 2 * (4 + t4));
+            mma16816(d, fa, bf, d);
+            bf[0] = ld32(x + 2 * (18 + t4));
+            bf[1] = ld32(x + 2 * ((20 + t4) & 31));
+            mma16816(d, fb, bf, d);
+            acc.v[nt][0] = fmaf(da_e, d[0], acc.v[nt][0]);
+            acc.v[nt][1] = fmaf(da_e, d[1], acc.v[nt][1]);
+            acc.v[nt][2] = fmaf(db_e, d[2], acc.v[nt][2]);
+            acc.v[nt][3] = fmaf(db_e, d[3], acc.v[nt][3]);
+        }
+        // ---- odd block: words are aligned with k = 0 (mod 4) -> one 64-bit load per fragment
+        q8_to_h2(ao1, fa[0], fa[2]);
+        q8_to_h2(bo1, fa[1], fa[3]);
+        q8_to_h2(ao2, fb[0], fb[2]);
+        q8_to_h2(bo2, fb[1], fb[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint8_t* x = s.xrow[nt] + 2 * (kb + 32);
+            const float2 c = ld64f(s.tbl + ((kb >> 5) + 1) * s.tpad + 8 * nt + 2 * L.t);
+            float d[4] = {c.x, c.y, c.x, c.y};
+            uint2 v = ld64(x + 2 * t4);
+            uint32_t bf[2] = {v.x, v.y};
+            mma16816(d, fa, bf, d);
+            v = ld64(x + 2 * (16 + t4));
+            bf[0] = v.x;
+            bf[1] = v.y;
+            mma16816(d, fb, bf, d);
+            acc.v[nt][0] = fmaf(da_o, d[0], acc.v[nt][0]);
+            acc.v[nt][1] = fmaf(da_o, d[1], acc.v[nt][1]);
+            acc.v[nt][2] = fmaf(db_o, d[2], acc.v[nt][2]);
+            acc.v[nt][3] = fmaf(db_o, d[3], acc.v[nt][3]);
+        }
+    }
+}
+
+// =============================================================================================
+// Q4_K
+// =============================================================================================
+// prep: lanes decode the 16-byte block headers of the stage (d, dmin, 6-bit scales/mins,
+// q4_k_ref.c:174-186) into fp32, once per (row, block) instead of once per lane:
+//   scratch[(row * CHUNK_BLOCKS + blk)][c] = float4(d*sc[2c], d*sc[2c+1], dmin*m[2c] + 1024*d*sc[2c],
+//                                                    dmin*m[2c+1] + 64*d*sc[2c+1])
+GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
+    using G = Geo<1>;
+    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+        const int row = p & 15, blk = p >> 4;
+        const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
+        const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
+        const uint32_t u0 = h.y, u1 = h.z, u2 = h.w;
+        const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;
+        const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);
+        const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
+        float4* out = reinterpret_cast<float4*>(s.scratch + (row * G::CHUNK_BLOCKS + blk) * 64);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t scw = (c < 2) ? sc_lo : sc_hi, mw = (c < 2) ? m_lo : m_hi;
+            const int sh = 16 * (c & 1);
+            const float s_e = d * static_cast<float>((scw >> sh) & 0xff);
+            const float s_o = d * static_cast<float>((scw >> (sh + 8)) & 0xff);
+            const float m_e = dmin * static_cast<float>((mw >> sh) & 0xff);
+            const float m_o = dmin * static_cast<float>((mw >> (sh + 8)) & 0xff);
+            float4 v;
+            v.x = s_e;
+            v.y = s_o;
+            v.z = fmaf(1024.f, s_e, m_e);
+            v.w = fmaf(64.f, s_o, m_o);
+            out[c] = v;
+        }
+    }
+}
+
+// One 32-bit word = 4 bytes = 4 low nibbles (sub-block 2c) + 4 high nibbles (sub-block 2c+1).
+// Swapping bytes 1 and 2 first makes each fp16 pair hold two CONSECUTIVE weights.
+GGQ_DEV void q4_to_h2(uint32_t w, uint32_t& lo01, uint32_t& lo23, uint32_t& hi01, uint32_t& hi23) {
+    const uint32_t p = prmt(w, w, 0x3120);
+    const uint32_t p8 = p >> 8;
+    lo01 = (p & 0x000F000Fu) | 0x64006400u;   // 1024 + q
+    lo23 = (p8 & 0x000F000Fu) | 0x64006400u;
+    hi01 = (p & 0x00F000F0u) | 0x54005400u;   // 64 + q
+    hi23 = (p8 & 0x00F000F0u) | 0x54005400u;
+}
+
+template <int NT>
+GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
+    using G = Geo<1>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < s.nblk; ++i) {
+        const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
+        const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
+        const uint8_t* sc0 = s.scratch + (L.g * G::CHUNK_BLOCKS + i) * 64;
+        const uint8_t* sc1 = sc0 + 8 * G::CHUNK_BLOCKS * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
+            const float4 sa = ld128f(sc0 + 16 * c), sb = ld128f(sc1 + 16 * c);
+            uint32_t e1[4], e2[4], o1[4], o2[4];  // A fragments: even/odd sub-block, first/second k16 step
+            q4_to_h2(wa.x, e1[0], e1[2], o1[0], o1[2]);
+            q4_to_h2(wb.x, e1[1], e1[3], o1[1], o1[3]);
+            q4_to_h2(wa.y, e2[0], e2[2], o2[0], o2[2]);
+            q4_to_h2(wb.y, e2[1], e2[3], o2[1], o2[3]);
+            const int kb = s.k0 + 256 * i + 64 * c;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint4 xe = ld128(s.xrow[nt] + 2 * (kb + 8 * L.t));
+                const uint4 xo = ld128(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t));
+                const float* tb = s.tbl + (kb >> 5) * s.tpad + 8 * nt + 2 * L.t;
+                const float2 se = ld64f(tb), so = ld64f(tb + s.tpad);
+                float de[4], dd[4];
+                uint32_t bf[2] = {xe.x, xe.y};
+                mma16816(de, e1, bf, zero);
+                bf[0] = xe.z;
+                bf[1] = xe.w;
+                mma16816(de, e2, bf, de);
+                bf[0] = xo.x;
+                bf[1] = xo.y;
+                mma16816(dd, o1, bf, zero);
+                bf[0] = xo.z;
+                bf[1] = xo.w;
+                mma16816(dd, o2, bf, dd);
+                float a0 = acc.v[nt][0], a1 = acc.v[nt][1], a2 = acc.v[nt][2], a3 = acc.v[nt][3];
+                a0 = fmaf(sa.x, de[0], a0);
+                a1 = fmaf(sa.x, de[1], a1);
+                a2 = fmaf(sb.x, de[2], a2);
+                a3 = fmaf(sb.x, de[3], a3);
+                a0 = fmaf(sa.y, dd[0], a0);
+                a1 = fmaf(sa.y, dd[1], a1);
+                a2 = fmaf(sb.y, dd[2], a2);
+                a3 = fmaf(sb.y, dd[3], a3);
+                a0 = fmaf(-sa.z, se.x, a0);
+                a1 = fmaf(-sa.z, se.y, a1);
+                a2 = fmaf(-sb.z, se.x, a2);
+                a3 = fmaf(-sb.z, se.y, a3);
+                a0 = fmaf(-sa.w, so.x, a0);
+                a1 = fmaf(-sa.w, so.y, a1);
+                a2 = fmaf(-sb.w, so.x, a2);
+                a3 = fmaf(-sb.w, so.y, a3);
+                acc.v[nt][0] = a0;
+                acc.v[nt][1] = a1;
+                acc.v[nt][2] = a2;
+                acc.v[nt][3] = a3;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Q6_K
+// =============================================================================================
+// prep: scratch[(row * CHUNK_BLOCKS + blk)][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh]  (fp32, exact)
+GGQ_DEV void prep_q6_k(const Lane& L, const StageArgs& s) {
+    using G = Geo<2>;
+    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+        const int row = p & 15, blk = p >> 4;
+        const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
+        const float d = h2f(ld16(b + 208));
+        float* out = reinterpret_cast<float*>(s.scratch + (row * G::CHUNK_BLOCKS + blk) * 64);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {  // scales 2jj, 2jj+1
+            const uint32_t two = ld16(b + 192 + 2 * jj);
+            const float s0 = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two & 0xff)));
+            const float s1 = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two >> 8)));
+            // sub-block j = 8h + 2grp + lh  ->  slot (h*2 + lh)*4 + grp
+            const int j0 = 2 * jj;  // lh = 0
+            const int h = j0 >> 3, grp = (j0 >> 1) & 3;
+            out[(h * 2 + 0) * 4 + grp] = s0;
+            out[(h * 2 + 1) * 4 + grp] = s1;
+        }
+    }
+}
+
+// 32-bit load at a 2-byte aligned address (odd blocks of a Q6_K row start at 2 mod 4).
+template <bool ODD> GGQ_DEV uint32_t ldw(const uint8_t* p) {
+    if (!ODD) return ld32(p);
+    const uint8_t* a = p - 2;
+    return funnelshift_r(ld32(a), ld32(a + 4), 16);
+}
+
+// ql word A (elements l..l+3 of groups 0 and 2), ql word B (groups 1 and 3), qh word -> four words of
+// 6-bit quants, one per group (q6_k_ref.c:320-336)
+GGQ_DEV void q6_bytes(uint32_t qla, uint32_t qlb, uint32_t qh, uint32_t g[4]) {
+    g[0] = (qla & 0x0F0F0F0Fu) | ((qh << 4) & 0x30303030u);
+    g[1] = (qlb & 0x0F0F0F0Fu) | ((qh << 2) & 0x30303030u);
+    g[2] = ((qla >> 4) & 0x0F0F0F0Fu) | (qh & 0x30303030u);
+    g[3] = ((qlb >> 4) & 0x0F0F0F0Fu) | ((qh >> 2) & 0x30303030u);
+}
+
+template <int NT, bool ODD>
+GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const uint8_t* r0, const uint8_t* r1,
+                                Acc<NT>& acc) {
+    using G = Geo<2>;
+    const uint8_t* b0 = r0 + i * G::BLK;
+    const uint8_t* b1 = r1 + i * G::BLK;
+    const uint8_t* sc0 = s.scratch + (L.g * G::CHUNK_BLOCKS + i) * 64;
+    const uint8_t* sc1 = sc0 + 8 * G::CHUNK_BLOCKS * 64;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int lh = 0; lh < 2; ++lh) {
+            const int l = 16 * lh + 4 * L.t;
+            uint32_t ga[4], gb[4];
+            q6_bytes(ldw<ODD>(b0 + 64 * h + l), ldw<ODD>(b0 + 64 * h + 32 + l), ldw<ODD>(b0 + 128 + 32 * h + l), ga);
+            q6_bytes(ldw<ODD>(b1 + 64 * h + l), ldw<ODD>(b1 + 64 * h + 32 + l), ldw<ODD>(b1 + 128 + 32 * h + l), gb);
+            const float4 sa = ld128f(sc0 + 16 * (h * 2 + lh)), sb = ld128f(sc1 + 16 * (h * 2 + lh));
+            const float sca[4] = {sa.x, sa.y, sa.z, sa.w}, scb[4] = {sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {
+                uint32_t fa[4];
+                fa[0] = prmt(ga[grp], 0x64646464u, 0x5140);  // 1024 + q6
+                fa[2] = prmt(ga[grp], 0x64646464u, 0x7362);
+                fa[1] = prmt(gb[grp], 0x64646464u, 0x5140);
+                fa[3] = prmt(gb[grp], 0x64646464u, 0x7362);
+                const int kk = s.k0 + 256 * i + 128 * h + 32 * grp + l;  // this lane's first activation
+                const int j16 = (s.k0 + 256 * i) / 16 + 8 * h + 2 * grp + lh;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint2 xv = ld64(s.xrow[nt] + 2 * kk);
+                    const float2 c = ld64f(s.tbl + j16 * s.tpad + 8 * nt + 2 * L.t);
+                    float d[4] = {c.x, c.y, c.x, c.y};
+                    const uint32_t bf[2] = {xv.x, xv.y};
+                    mma16816(d, fa, bf, d);
+                    acc.v[nt][0] = fmaf(sca[grp], d[0], acc.v[nt][0]);
+                    acc.v[nt][1] = fmaf(sca[grp], d[1], acc.v[nt][1]);
+                    acc.v[nt][2] = fmaf(scb[grp], d[2], acc.v[nt][2]);
+                    acc.v[nt][3] = fmaf(scb[grp], d[3], acc.v[nt][3]);
+                }
+            }
+        }
+    }
+}
+
+template <int NT>
+GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
+    using G = Geo<2>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    for (int i = 0; i < s.nblk; i += 2) {  // chunk starts at an even block: even blocks 4-byte aligned
+        compute_q6_k_block<NT, false>(L, s, i, r0, r1, acc);
+        compute_q6_k_block<NT, true>(L, s, i + 1, r0, r1, acc);
+    }
+}
+
+// ---- format dispatch ---------------------------------------------------------------------------
+template <int FMT, int NT> struct Tile;
+template <int NT> struct Tile<0, NT> {
+    static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q8_0<NT>(L, s, a); }
+};
+template <int NT> struct Tile<1, NT> {
+    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k(L, s); }
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q4_k<NT>(L, s, a); }
+};
+template <int NT> struct Tile<2, NT> {
+    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k(L, s); }
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q6_k<NT>(L, s, a); }
+};
+
+}  // namespace dec
+}  // namespace ggq

@@ -1,0 +1,108 @@
+/*
+ * ggq.h — C ABI of the B200-native GGUF mmq path (libggq.so).
+ *
+ * This is the drop-in boundary for ONE hot path of PowerfulGhost/gguf-triton-kernel: multiplying
+ * GGUF block-quantized weights (Q8_0 / Q4_K / Q6_K) by fp16 activations.  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - All data pointers are DEVICE pointers on the device that is current on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls enqueue work
+ *     on that stream and return; they never synchronize, never allocate device memory and never
+ *     throw.  (The reference launches its Triton kernels the same way: asynchronously on the
+ *     current stream, kernels/mmq_q8_0.py:133-147.)
+ *   - Return value: 0 on success; a positive value is a cudaError_t from the launch; a negative
+ *     value is one of GGQ_E_* (argument errors, detected before anything is enqueued).
+ *   - Naming: O = out-features (reference arg `M`, rows of the packed weight), T = tokens (reference
+ *     arg `N`, rows of the activation), K = in-features.  C[T, O] = X[T, K] . dequant(W)[O, K]^T.
+ *   - Packed weight W: row-major rows of K/QK blocks, exactly the byte stream the reference packers
+ *     emit (utils/quantize/q8_0.py:41-47; q4_k_ref.c:76-89 `block_q4_K`; q6_k_ref.c:62-68
+ *     `block_q6_K`).  No repacking, no alignment requirement beyond what cudaMalloc/torch give the
+ *     base pointer; shapes whose rows are not 16-byte multiples take a slower general kernel.
+ *   - Arithmetic: fp16 activations (NOT re-quantized to Q8_1), fp32 accumulation, fp16 output.
+ */
+#ifndef GGQ_H_
+#define GGQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGQ_VERSION 100 /* 0.1.0 */
+
+/* argument errors (negative so they cannot collide with cudaError_t) */
+#define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
+                             /* kernels/mmq_q8_0.py:124, mmq_q4_k.py:263, mmq_q6_k.py:211), or     */
+                             /* O/T/K/ldc negative or out of range                                  */
+#define GGQ_E_POINTER   (-2) /* NULL data pointer with a non-empty problem                          */
+#define GGQ_E_FAMILY    (-3) /* requested kernel family cannot run this shape                       */
+#define GGQ_E_FORMAT    (-4) /* unknown quant format id                                             */
+
+/* quant formats */
+#define GGQ_Q8_0 0 /* 32 weights / 34 B:  fp16 d, int8 qs[32]                                       */
+#define GGQ_Q4_K 1 /* 256 weights / 144 B: fp16 d, fp16 dmin, 12 B 6-bit scales+mins, qs[128]       */
+#define GGQ_Q6_K 2 /* 256 weights / 210 B: ql[128], qh[64], int8 scales[16], fp16 d                 */
+
+/* kernel families (ggq_mm_ex `family`) */
+#define GGQ_FAMILY_AUTO    0 /* decode for T<=16 (when the shape is aligned), prefill for large T   */
+#define GGQ_FAMILY_GENERIC 1 /* any shape, any alignment; one warp per output row                    */
+#define GGQ_FAMILY_DECODE  2 /* HBM-bound skinny GEMM, T<=16: TMA bulk-staged packed rows,           */
+                             /* register unpack, mma.sync m16n8k16 f16->f32                           */
+#define GGQ_FAMILY_PREFILL 3 /* tensor-bound GEMM: packed tiles -> smem dequant -> tcgen05.mma/TMEM   */
+
+/*
+ * mmq entry points.  Replace the bodies of
+ *     kernels/mmq_q8_0.py:102  mmq_q8_0(A, B, M, N, K)   (+ Triton kernel :13-93)
+ *     kernels/mmq_q4_k.py:240  mmq_q4_k(A, B, M, N, K)   (+ Triton kernels :30-229)
+ *     kernels/mmq_q6_k.py:197  mmq_q6_k(A, B, M, N, K)   (+ Triton kernels :28-186)
+ * with  W = A.data_ptr(), X = B.data_ptr(), O = M, T = N.  C is the fp16 [T, O] contiguous output the
+ * reference allocates at mmq_q8_0.py:128 (element [t, o] at O*t + o, :91).
+ */
+int ggq_mm_q8_0_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream);
+int ggq_mm_q4_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream);
+int ggq_mm_q6_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T, int64_t K, void* stream);
+
+/*
+ * Extended form used by the tests (family pinning), the N-split multi-GPU driver (ldc / peer
+ * outputs) and the benchmarks.
+ *   fmt     GGQ_Q8_0 | GGQ_Q4_K | GGQ_Q6_K
+ *   ldx     row stride of X in elements (>= K)
+ *   ldc     row stride of every output in elements (>= O); element [t, o] is written at ldc*t + o
+ *   n_out   number of output buffers (1..8); the same tile is stored to every C_out[i].  With
+ *           n_out > 1 the extra pointers are peer-mapped buffers of the other ranks (NVLink), which
+ *           fuses the N-split all-gather into the epilogue.
+ *   family  GGQ_FAMILY_*
+ */
+int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc,
+              int64_t O, int64_t T, int64_t K, int family, void* stream);
+
+/*
+ * Dequantize packed rows to fp16 [O, K] with the SAME device functions the prefill GEMM uses.
+ * Bit-exact targets: utils/quantize/q8_0.py:52-100 dequantize_q8_0, q4_k.py:146-158 dequantize_q4_k,
+ * q6_k.py:138-159 dequantize_q6_k (fp32 there; `.half()` of it here).
+ */
+int ggq_dequant_q8_0_f16(const void* W, void* out, int64_t O, int64_t K, void* stream);
+int ggq_dequant_q4_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream);
+int ggq_dequant_q6_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream);
+
+/* Bytes of a packed [O, K] weight (O * K/QK * block bytes), or GGQ_E_* (<0). */
+int64_t ggq_packed_nbytes(int fmt, int64_t O, int64_t K);
+
+/* Which family GGQ_FAMILY_AUTO resolves to for this problem (GGQ_FAMILY_*), or GGQ_E_* (<0). */
+int ggq_select_family(int fmt, int64_t O, int64_t T, int64_t K);
+
+/* Kernels launched by this library since load (all families; for bench.py's `gpu_launches`). */
+int64_t ggq_launch_count(void);
+
+/* Static description of an error code returned by any function above. */
+const char* ggq_error_string(int code);
+
+int ggq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGQ_H_ */

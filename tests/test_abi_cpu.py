@@ -1,0 +1,79 @@
+"""CPU-only checks of the drop-in boundary: libggq.so loads, exports every symbol include/ggq.h
+declares, answers its pure-host queries, and the Python entry points keep the reference's names,
+constants and error behaviour.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gguf-triton-kernel_b200", "libggq.so")
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ggq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ggq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "libggq.so not built (make -C gguf-triton-kernel_b200)"
+    lib = ctypes.CDLL(LIB)
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in ggq.h but not exported"
+
+
+def test_host_queries():
+    from kernels import _ext
+    L = _ext.lib()
+    assert L.ggq_version() == 100
+    assert L.ggq_packed_nbytes(0, 4096, 4096) == 17825792          # BASELINE config 1
+    assert L.ggq_packed_nbytes(1, 128256, 4096) == 295501824       # config 2
+    assert L.ggq_packed_nbytes(2, 4096, 14336) == 48168960         # config 3
+    assert L.ggq_packed_nbytes(1, 4, 100) == -1 and L.ggq_packed_nbytes(7, 4, 256) == -4
+    assert L.ggq_select_family(1, 4096, 1, 4096) == _ext.FAMILY_DECODE
+    assert L.ggq_select_family(0, 16, 1, 32) == _ext.FAMILY_GENERIC      # 34-byte rows: unaligned
+    assert L.ggq_select_family(2, 16, 4, 256) == _ext.FAMILY_GENERIC     # 210-byte rows
+    assert b"shape" in L.ggq_error_string(-1)
+    assert L.ggq_launch_count() == 0
+
+
+def test_argument_errors_are_reported_without_a_device():
+    from kernels import _ext
+    L = _ext.lib()
+    one = ctypes.c_void_p(256)
+    assert L.ggq_mm_q8_0_f16(one, one, one, 4, 1, 33, None) == -1       # K % 32 (mmq_q8_0.py:124)
+    assert L.ggq_mm_q4_k_f16(one, one, one, 4, 1, 128, None) == -1      # K % 256 (mmq_q4_k.py:263)
+    assert L.ggq_mm_q6_k_f16(one, one, one, 4, 1, 255, None) == -1      # K % 256 (mmq_q6_k.py:211)
+    assert L.ggq_mm_q4_k_f16(None, one, one, 4, 1, 256, None) == -2
+    assert L.ggq_mm_q4_k_f16(None, None, None, 0, 1, 256, None) == 0    # empty problem: nothing to do
+    outs = (ctypes.c_void_p * 1)(256)
+    assert L.ggq_mm_ex(1, one, one, 256, outs, 1, 4, 4, 1, 256, 9, None) == -3
+    assert L.ggq_mm_ex(1, one, one, 128, outs, 1, 4, 4, 1, 256, 0, None) == -1  # ldx < K
+
+
+@pytest.mark.parametrize("mod,fn,consts", [
+    ("kernels.mmq_q8_0", "mmq_q8_0", dict(QK8_0=32, QK8_1=32, Q8_0_SIZE=34)),
+    ("kernels.mmq_q4_k", "mmq_q4_k", dict(Q4_K_BLOCK_SIZE=144, Q8_1_BLOCK_SIZE=36, Q4_K_SUBBLK_NUM=8, QK_K=256, QK8_1=32)),
+    ("kernels.mmq_q6_k", "mmq_q6_k", dict(QK_K=256, Q6_K_SUBBLK_NUM=16, QK8_1=32, Q6_K_BLOCK_SIZE=210, Q8_1_BLOCK_SIZE=36)),
+])
+def test_entry_points_mirror_the_reference(mod, fn, consts):
+    import importlib
+    import inspect
+    m = importlib.import_module(mod)
+    f = getattr(m, fn)
+    assert list(inspect.signature(f).parameters) == ["A", "B", "M", "N", "K"]
+    for k, v in consts.items():
+        assert getattr(m, k) == v
+    A = torch.zeros(144, dtype=torch.int8)
+    B = torch.zeros((1, 100), dtype=torch.float16)
+    with pytest.raises(AssertionError):          # the reference's only check: K % block
+        f(A, B, 1, 1, 100)
+    K = 256
+    with pytest.raises(ValueError):              # CPU tensors: there is no CPU path
+        f(torch.zeros(1 * (K // consts.get("QK8_0", 256)) * (34 if "Q8_0_SIZE" in consts else 1), dtype=torch.int8),
+          torch.zeros((1, K), dtype=torch.float16), 1, 1, K)
