@@ -148,6 +148,22 @@ int ggq_select_family(int fmt, int64_t O, int64_t T, int64_t K) {
     return select_family(fmt, a);
 }
 
+int ggq_decode_plan(int fmt, int64_t O, int64_t T, int64_t K, int* out9) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 1 || T < 1 || K < fmt_qk(fmt) || K % fmt_qk(fmt) != 0 || !out9) return GGQ_E_SHAPE;
+    MmArgs a{};
+    a.W = reinterpret_cast<const uint8_t*>(uintptr_t{256});
+    a.X = reinterpret_cast<const void*>(uintptr_t{256});
+    a.n_out = 1;
+    a.ldx = K;
+    a.ldc = O;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    if (!decode_supports(fmt, a)) return GGQ_E_FAMILY;
+    return decode_plan(fmt, a, out9);
+}
+
 int64_t ggq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* ggq_error_string(int code) {

@@ -54,7 +54,7 @@ template <int FMT, int NT, int AT>
 __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
     using G = Geo<FMT>;
     constexpr int STAGE_BYTES = 16 * G::SLOT;
-    constexpr int SCR_BYTES = 16 * G::CHUNK_BLOCKS * G::SCRATCH_PER_BLOCK;
+    constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
     constexpr int TPAD = 8 * NT;
     extern __shared__ __align__(128) uint8_t smem[];
 
@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
     __syncthreads();
 
     const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
+    // live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA
     auto tile_of = [&](int batch, int a) -> int64_t {
-        return (static_cast<int64_t>(batch) * gridDim.x + blockIdx.x) * (WT * AT) + tg * AT + a;
+        return (static_cast<int64_t>(batch * AT + a) * gridDim.x + blockIdx.x) * WT + tg;
     };
     auto slice_chunks = [&](int slice) { return min(p.cps, p.nc - slice * p.cps); };
 
@@ -178,20 +179,23 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
                     mbar_wait(my_full + cstage, (full_phase >> cstage) & 1u);
                     full_phase ^= 1u << cstage;
                     const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
+                    const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
                     StageArgs s;
                     s.rows = ring + cstage * STAGE_BYTES;
-                    s.data_off = (b0 * G::BLK) & 15;
-                    s.nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
                     s.xrow[0] = xs + tok0 * p.x_stride;
                     s.xrow[1] = xs + tok1 * p.x_stride;
-                    s.k0 = ci * G::CHUNK_ELEMS;
                     s.tbl = tbl;
                     s.tpad = TPAD;
                     s.scratch = scr;
-                    Tile<FMT, NT>::prep(L, s);
-                    __syncwarp();
-                    Tile<FMT, NT>::compute(L, s, acc[a]);
-                    __syncwarp();  // all lanes are done reading the stage and the scratch
+                    for (int b = 0; b < nblk; b += G::PREP_BLOCKS) {
+                        s.data_off = ((b0 * G::BLK) & 15) + b * G::BLK;
+                        s.nblk = min(G::PREP_BLOCKS, nblk - b);
+                        s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
+                        Tile<FMT, NT>::prep(L, s);
+                        __syncwarp();
+                        Tile<FMT, NT>::compute(L, s, acc[a]);
+                        __syncwarp();  // all lanes are done reading the stage and the scratch
+                    }
                     if (!pc.done) {
                         issue(pc, cstage);
                         pc.ci += KW;
@@ -204,26 +208,24 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
 
         // ---- epilogue: (reduce over the KW warps of a tile,) round to fp16, store -----------------
         if (KW > 1) {
-            __syncthreads();  // previous batch's readers of `red` are done
 #pragma unroll
-            for (int a = 0; a < AT; ++a)
+            for (int a = 0; a < AT; ++a) {
+                __syncthreads();  // previous readers of `red` are done
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        red[(((w * AT + a) * NT + nt) * 4 + i) * 32 + lane] = acc[a].v[nt][i];
-            __syncthreads();
-            if (sub == 0) {
-#pragma unroll
-                for (int a = 0; a < AT; ++a)
+                    for (int i = 0; i < 4; ++i) red[((w * NT + nt) * 4 + i) * 32 + lane] = acc[a].v[nt][i];
+                __syncthreads();
+                if (sub == 0) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             float v = acc[a].v[nt][i];
-                            for (int k = 1; k < KW; ++k) v += red[((((w + k) * AT + a) * NT + nt) * 4 + i) * 32 + lane];
+                            for (int k = 1; k < KW; ++k) v += red[(((w + k) * NT + nt) * 4 + i) * 32 + lane];
                             acc[a].v[nt][i] = v;
                         }
+                }
             }
         }
         if (sub == 0) {
@@ -283,7 +285,7 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     const int wt = NW / kw;
 
     constexpr int STAGE_BYTES = 16 * G::SLOT;
-    constexpr int SCR_BYTES = 16 * G::CHUNK_BLOCKS * G::SCRATCH_PER_BLOCK;
+    constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
     const uint32_t xpad = (FMT == 1) ? 64u : 32u;  // x row pitch = 64 (128-bit loads) / 32 (64-bit loads) mod 128
     auto layout = [&](int cps, int stages, int at, bool commit) -> size_t {
         const size_t elems = static_cast<size_t>(cps) * G::CHUNK_ELEMS;
@@ -295,7 +297,8 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
         const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
         const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
         const size_t o_scr = take(static_cast<size_t>(NW) * SCR_BYTES);
-        const size_t o_red = take(kw > 1 ? static_cast<size_t>(NW) * at * pl.nt * 4 * 32 * 4 : 0);
+        const size_t o_red = take(kw > 1 ? static_cast<size_t>(NW) * pl.nt * 4 * 32 * 4 : 0);
+        (void)at;
         if (commit) {
             p.x_stride = xstride;
             p.off_bars = static_cast<uint32_t>(o_bars);
@@ -325,8 +328,9 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     p.stages = stages;
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
-    pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt * at - 1) / (wt * at)));
-    p.num_batches = (p.num_tiles + pl.grid * wt * at - 1) / (pl.grid * wt * at);
+    pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt - 1) / wt));
+    const int rounds = (p.num_tiles + pl.grid * wt - 1) / (pl.grid * wt);
+    p.num_batches = (rounds + at - 1) / at;
     return true;
 }
 
@@ -371,6 +375,24 @@ bool decode_supports(int fmt, const MmArgs& a) {
     const int64_t nb = a.K / fmt_qk(fmt);
     if ((nb * fmt_blk(fmt)) & 15) return false;  // rows must be whole 16-byte vectors (Q8_0 / Q6_K: nb % 8 == 0)
     return true;
+}
+
+// Host-only view of the decode planner (tests / DESIGN.md): out = {KW, AT, NT, slices, chunks per
+// slice, stages, grid, batches, smem bytes}.  Returns 0, or GGQ_E_FAMILY when no plan fits.
+int decode_plan(int fmt, const MmArgs& a, int* out) {
+    dec::Plan pl;
+    const int T = static_cast<int>(a.T > 16 ? 16 : a.T);
+    bool ok = false;
+    switch (fmt) {
+        case GGQ_Q8_0: ok = dec::make_plan<0>(a, T, pl); break;
+        case GGQ_Q4_K: ok = dec::make_plan<1>(a, T, pl); break;
+        case GGQ_Q6_K: ok = dec::make_plan<2>(a, T, pl); break;
+    }
+    if (!ok) return GGQ_E_FAMILY;
+    const int v[9] = {pl.p.KW, pl.at, pl.nt, pl.p.n_slices, pl.p.cps, pl.p.stages, pl.grid, pl.p.num_batches,
+                      static_cast<int>(pl.smem)};
+    for (int i = 0; i < 9; ++i) out[i] = v[i];
+    return 0;
 }
 
 int launch_decode(int fmt, const MmArgs& a) {

@@ -6,13 +6,17 @@
 // raw fp16 activation rows (also TMA-staged), and block / sub-block scales are applied to the fp32
 // MMA result ("post-scaling"), so dequantized weights never exist outside registers:
 //
-//   Q8_0  A = 1152 + q  (0x6400 | (q ^ 0x80)),  D starts at -1152*sum32(x);   acc += d * D
-//   Q4_K  A = 1024 + q  (low nibbles) / 64 + q (high nibbles, 0x5400 | (q << 4));
-//         acc += (d*sc_j) * D_j - (dmin*m_j + bias_j*d*sc_j) * sum32_j(x)
-//   Q6_K  A = 1024 + q6 (0x6400 | q6),          D starts at -1056*sum16(x);   acc += (d*sc_j) * D_j
+//   Q8_0  A = (q + 128) * 2^-24,   D starts at -128 * 2^-24 * sum32(x);   acc += (d * 2^24) * D
+//   Q4_K  A = q * 2^-24 (low nibbles) / q * 2^-20 (high nibbles, in place);
+//         acc += (d*sc_j * 2^24|2^20) * D_j - (dmin*m_j) * sum32_j(x)
+//   Q6_K  A = q6 * 2^-24,           D starts at -32 * 2^-24 * sum16(x);    acc += (d*sc_j * 2^24) * D_j
 //
-// The integer->fp16 "magic bias" costs one LOP3/PRMT per weight pair; products are exact in the
-// tensor core and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
+// Integer -> fp16 costs one LOP3/PRMT per weight PAIR: an integer < 1024 placed in the low mantissa
+// bits of a half whose exponent field is zero IS the subnormal value n * 2^-24, which the tensor core
+// multiplies exactly; the power of two is folded into the fp32 scale.  (The classic 0x6400 "1024 + n"
+// magic is avoided on purpose: HMMA truncates when it aligns addends, so a bias of 1024 costs ~10 bits
+// of the fp32 accumulator — measured 2e-4 relative error on B200 — while the subnormal form keeps the
+// addends at the magnitude of the signal.)  Products are exact and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
 // agree, lane t of a quad always takes the 4 weights that share one 32-bit word and the 4 matching
 // consecutive activations.
 //
@@ -53,21 +57,24 @@ namespace dec {
 template <int FMT> struct Geo;
 template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B; lanes read 32-bit words: slot/4 % 32 == 12
     static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = 16, CHUNK_ELEMS = 512, CHUNK_BYTES = 544, SLOT = 560;
+    static constexpr int PREP_BLOCKS = 16;      // blocks handled per prep/compute sub-step of a stage
     static constexpr int GROUP = 32;            // activations per pre-summed group (one block)
     static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
-    static constexpr float TBL_MUL = -1152.f;
+    static constexpr float TBL_MUL = -128.f / 16777216.f;   // cancels the +128 of (q ^ 0x80)
 };
 template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B; lanes read 64-bit: slot % 128 == 96
     static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 608;
+    static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 32;
     static constexpr int SCRATCH_PER_BLOCK = 64;
     static constexpr float TBL_MUL = 1.f;
 };
 template <> struct Geo<2> {  // Q6_K: 2 blocks = 512 weights = 420 B (+ up to 12 B of alignment slack)
     static constexpr int QK = 256, BLK = 210, CHUNK_BLOCKS = 2, CHUNK_ELEMS = 512, CHUNK_BYTES = 420, SLOT = 464;
+    static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 16;
     static constexpr int SCRATCH_PER_BLOCK = 64;
-    static constexpr float TBL_MUL = -1056.f;
+    static constexpr float TBL_MUL = -32.f / 16777216.f;    // the -32 of (q6 - 32)
 };
 
 struct Lane {
@@ -77,13 +84,13 @@ struct Lane {
 // What one warp needs to consume one stage.
 struct StageArgs {
     const uint8_t* rows;      // stage base: 16 row slots of Geo::SLOT bytes
-    int data_off;             // byte offset of the chunk inside every slot (alignment slack)
-    int nblk;                 // blocks in this chunk (<= CHUNK_BLOCKS; even for Q8_0 / Q6_K)
+    int data_off;             // byte offset of this sub-step's first block inside every slot
+    int nblk;                 // blocks in this sub-step (<= PREP_BLOCKS; even for Q8_0 / Q6_K)
     const uint8_t* xrow[2];   // per n-tile: this lane's activation row (token), at slice-relative k = 0
-    int k0;                   // slice-relative element index of the chunk's first weight
+    int k0;                   // slice-relative element index of the sub-step's first weight
     const float* tbl;         // [k / GROUP][TPAD] pre-summed activations times Geo::TBL_MUL
     int tpad;                 // 8 * NT
-    uint8_t* scratch;         // this warp's prepared-scale area (SCRATCH_PER_BLOCK * 16 * CHUNK_BLOCKS)
+    uint8_t* scratch;         // this warp's prepared-scale area (SCRATCH_PER_BLOCK * 16 * PREP_BLOCKS)
 };
 
 GGQ_DEV uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
@@ -106,8 +113,8 @@ template <int NT> struct Acc {
 // second word is rebuilt as [q30 q31 q0 q1] from words 8 and 0.  odd block: words 9+t and 13+t.
 GGQ_DEV void q8_to_h2(uint32_t w, uint32_t& lo, uint32_t& hi) {
     const uint32_t u = w ^ 0x80808080u;       // q + 128 in every byte
-    lo = prmt(u, 0x64646464u, 0x5140);        // halves (0x64|u0, 0x64|u1) = 1152 + q
-    hi = prmt(u, 0x64646464u, 0x7362);
+    lo = prmt(u, 0u, 0x5140);                 // halves (0x00|u0, 0x00|u1) = (q + 128) * 2^-24
+    hi = prmt(u, 0u, 0x7362);
 }
 
 template <int NT>
@@ -125,8 +132,8 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
         uint32_t be1 = ld32(b + 4 + t4), be2 = ld32(b + 20 + t4), bo1 = ld32(b + 36 + t4), bo2 = ld32(b + 52 + t4);
         ae2 = prmt(ae2, a0w, wrap_sel);
         be2 = prmt(be2, b0w, wrap_sel);
-        const float da_e = h2f(a0w & 0xffffu), da_o = h2f(a8w >> 16);
-        const float db_e = h2f(b0w & 0xffffu), db_o = h2f(b8w >> 16);
+        const float da_e = h2f(a0w & 0xffffu) * 16777216.f, da_o = h2f(a8w >> 16) * 16777216.f;
+        const float db_e = h2f(b0w & 0xffffu) * 16777216.f, db_o = h2f(b8w >> 16) * 16777216.f;
         const int kb = s.k0 + 64 * p;  // first weight of the even block (slice relative)
         uint32_t fa[4], fb[4];         // A fragments of the two k16 steps of a block
         // ---- even block: activations start at k = 2 (mod 4) -> two 32-bit loads per fragment
@@ -181,8 +188,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // =============================================================================================
 // prep: lanes decode the 16-byte block headers of the stage (d, dmin, 6-bit scales/mins,
 // q4_k_ref.c:174-186) into fp32, once per (row, block) instead of once per lane:
-//   scratch[(row * CHUNK_BLOCKS + blk)][c] = float4(d*sc[2c], d*sc[2c+1], dmin*m[2c] + 1024*d*sc[2c],
-//                                                    dmin*m[2c+1] + 64*d*sc[2c+1])
+//   scratch[(row * PREP_BLOCKS + blk)][c] = float4(d*sc[2c] * 2^24, d*sc[2c+1] * 2^20, dmin*m[2c], dmin*m[2c+1])
 GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
     using G = Geo<1>;
     for (int p = L.lane; p < 16 * s.nblk; p += 32) {
@@ -193,7 +199,7 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
         const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;
         const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);
         const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
-        float4* out = reinterpret_cast<float4*>(s.scratch + (row * G::CHUNK_BLOCKS + blk) * 64);
+        float4* out = reinterpret_cast<float4*>(s.scratch + (row * G::PREP_BLOCKS + blk) * 64);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint32_t scw = (c < 2) ? sc_lo : sc_hi, mw = (c < 2) ? m_lo : m_hi;
@@ -203,10 +209,10 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
             const float m_e = dmin * static_cast<float>((mw >> sh) & 0xff);
             const float m_o = dmin * static_cast<float>((mw >> (sh + 8)) & 0xff);
             float4 v;
-            v.x = s_e;
-            v.y = s_o;
-            v.z = fmaf(1024.f, s_e, m_e);
-            v.w = fmaf(64.f, s_o, m_o);
+            v.x = s_e * 16777216.f;  // low nibbles enter the MMA as q * 2^-24
+            v.y = s_o * 1048576.f;   // high nibbles as q * 2^-20
+            v.z = m_e;
+            v.w = m_o;
             out[c] = v;
         }
     }
@@ -217,10 +223,10 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
 GGQ_DEV void q4_to_h2(uint32_t w, uint32_t& lo01, uint32_t& lo23, uint32_t& hi01, uint32_t& hi23) {
     const uint32_t p = prmt(w, w, 0x3120);
     const uint32_t p8 = p >> 8;
-    lo01 = (p & 0x000F000Fu) | 0x64006400u;   // 1024 + q
-    lo23 = (p8 & 0x000F000Fu) | 0x64006400u;
-    hi01 = (p & 0x00F000F0u) | 0x54005400u;   // 64 + q
-    hi23 = (p8 & 0x00F000F0u) | 0x54005400u;
+    lo01 = p & 0x000F000Fu;    // q * 2^-24 (fp16 subnormals)
+    lo23 = p8 & 0x000F000Fu;
+    hi01 = p & 0x00F000F0u;    // q * 2^-20
+    hi23 = p8 & 0x00F000F0u;
 }
 
 template <int NT>
@@ -232,8 +238,8 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     for (int i = 0; i < s.nblk; ++i) {
         const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
         const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
-        const uint8_t* sc0 = s.scratch + (L.g * G::CHUNK_BLOCKS + i) * 64;
-        const uint8_t* sc1 = sc0 + 8 * G::CHUNK_BLOCKS * 64;
+        const uint8_t* sc0 = s.scratch + (L.g * G::PREP_BLOCKS + i) * 64;
+        const uint8_t* sc1 = sc0 + 8 * G::PREP_BLOCKS * 64;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
@@ -291,14 +297,14 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // =============================================================================================
 // Q6_K
 // =============================================================================================
-// prep: scratch[(row * CHUNK_BLOCKS + blk)][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh]  (fp32, exact)
+// prep: scratch[(row * PREP_BLOCKS + blk)][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh] * 2^24  (fp32, exact)
 GGQ_DEV void prep_q6_k(const Lane& L, const StageArgs& s) {
     using G = Geo<2>;
     for (int p = L.lane; p < 16 * s.nblk; p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
-        const float d = h2f(ld16(b + 208));
-        float* out = reinterpret_cast<float*>(s.scratch + (row * G::CHUNK_BLOCKS + blk) * 64);
+        const float d = h2f(ld16(b + 208)) * 16777216.f;
+        float* out = reinterpret_cast<float*>(s.scratch + (row * G::PREP_BLOCKS + blk) * 64);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {  // scales 2jj, 2jj+1
             const uint32_t two = ld16(b + 192 + 2 * jj);
@@ -335,8 +341,8 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
     using G = Geo<2>;
     const uint8_t* b0 = r0 + i * G::BLK;
     const uint8_t* b1 = r1 + i * G::BLK;
-    const uint8_t* sc0 = s.scratch + (L.g * G::CHUNK_BLOCKS + i) * 64;
-    const uint8_t* sc1 = sc0 + 8 * G::CHUNK_BLOCKS * 64;
+    const uint8_t* sc0 = s.scratch + (L.g * G::PREP_BLOCKS + i) * 64;
+    const uint8_t* sc1 = sc0 + 8 * G::PREP_BLOCKS * 64;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -350,10 +356,10 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
 #pragma unroll
             for (int grp = 0; grp < 4; ++grp) {
                 uint32_t fa[4];
-                fa[0] = prmt(ga[grp], 0x64646464u, 0x5140);  // 1024 + q6
-                fa[2] = prmt(ga[grp], 0x64646464u, 0x7362);
-                fa[1] = prmt(gb[grp], 0x64646464u, 0x5140);
-                fa[3] = prmt(gb[grp], 0x64646464u, 0x7362);
+                fa[0] = prmt(ga[grp], 0u, 0x5140);  // q6 * 2^-24
+                fa[2] = prmt(ga[grp], 0u, 0x7362);
+                fa[1] = prmt(gb[grp], 0u, 0x5140);
+                fa[3] = prmt(gb[grp], 0u, 0x7362);
                 const int kk = s.k0 + 256 * i + 128 * h + 32 * grp + l;  // this lane's first activation
                 const int j16 = (s.k0 + 256 * i) / 16 + 8 * h + 2 * grp + lh;
 #pragma unroll

@@ -94,6 +94,11 @@ int64_t ggq_packed_nbytes(int fmt, int64_t O, int64_t K);
 /* Which family GGQ_FAMILY_AUTO resolves to for this problem (GGQ_FAMILY_*), or GGQ_E_* (<0). */
 int ggq_select_family(int fmt, int64_t O, int64_t T, int64_t K);
 
+/* Host-only: the decode family's static work decomposition for a problem (no GPU needed).
+ * out9 = {warps per tile, live tiles per warp, 8-token n-tiles, K-slices, chunks per slice, pipeline
+ * stages per warp, CTAs, batches, dynamic shared memory bytes}.  0, or GGQ_E_* (<0). */
+int ggq_decode_plan(int fmt, int64_t O, int64_t T, int64_t K, int* out9);
+
 /* Kernels launched by this library since load (all families; for bench.py's `gpu_launches`). */
 int64_t ggq_launch_count(void);
 
