@@ -37,6 +37,7 @@ static int validate(int fmt, const void* W, const void* X, void* const* C_out, i
 }
 
 static int select_family(int fmt, const MmArgs& a) {
+    if (a.O < 16) return GGQ_FAMILY_GENERIC;  // less than one 16-row MMA tile: one warp per row is the better fit
     if (a.T <= 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;
     if (a.T >= 64 && prefill_supports(fmt, a)) return GGQ_FAMILY_PREFILL;
     if (a.T > 16 && a.T < 64 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;  // looped over 16-token groups

@@ -29,9 +29,10 @@
 namespace ggq {
 namespace dec {
 
-constexpr int NW = 8;                     // warps per CTA
+constexpr int MAX_NW = 16;                // most warps per CTA of any configuration
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+constexpr int SMEM_LIMIT_2 = 113 * 1024;  // per CTA when two CTAs share an SM (228 KB - 2 x 1 KB reserved)
 
 struct Params {
     const uint8_t* W;
@@ -50,8 +51,9 @@ struct Params {
     uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red;
 };
 
-template <int FMT, int NT, int AT>
-__global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
+// NW warps per CTA, MINB CTAs per SM (register budget), NT 8-token n-tiles, AT live tiles per warp
+template <int FMT, int NT, int AT, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) decode_kernel(const Params p) {
     using G = Geo<FMT>;
     constexpr int STAGE_BYTES = 16 * G::SLOT;
     constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
@@ -108,11 +110,16 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
         const int64_t left = p.O - row0;
         const int nrows = left < 16 ? static_cast<int>(left) : 16;
         uint64_t* bar = my_full + stage;
-        if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(len * nrows));
-        __syncwarp();
-        if (lane < nrows)
-            bulk_g2s(ring + stage * STAGE_BYTES + lane * G::SLOT, p.W + (row0 + lane) * p.rowB + src,
-                     static_cast<uint32_t>(len), bar);
+        if (lane == 0) {  // one lane issues the whole stage: UBLKCP is a per-warp (uniform datapath) instruction
+            mbar_arrive_expect_tx(bar, static_cast<uint32_t>(len * nrows));
+            uint8_t* dst = ring + stage * STAGE_BYTES;
+            const uint8_t* from = p.W + row0 * p.rowB + src;
+            for (int r = 0; r < nrows; ++r) {
+                bulk_g2s(dst, from, static_cast<uint32_t>(len), bar);
+                dst += G::SLOT;
+                from += p.rowB;
+            }
+        }
     };
 
     Cur pc{0, 0, 0, sub, false};
@@ -185,7 +192,6 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
                     s.xrow[0] = xs + tok0 * p.x_stride;
                     s.xrow[1] = xs + tok1 * p.x_stride;
                     s.tbl = tbl;
-                    s.tpad = TPAD;
                     s.scratch = scr;
                     for (int b = 0; b < nblk; b += G::PREP_BLOCKS) {
                         s.data_off = ((b0 * G::BLK) & 15) + b * G::BLK;
@@ -254,12 +260,13 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_kernel(const Params p) {
 // ---- host side ------------------------------------------------------------------------------------
 struct Plan {
     Params p;
-    int nt, at, grid;
+    int nt, at, grid, nw, occ;
     size_t smem;
 };
 
+// One configuration attempt: NW warps per CTA, OCC CTAs per SM.
 template <int FMT>
-static bool make_plan(const MmArgs& a, int T, Plan& pl) {
+static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_slicing, Plan& pl) {
     using G = Geo<FMT>;
     Params& p = pl.p;
     p = Params{};
@@ -277,7 +284,10 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     p.nc = (p.nb + G::CHUNK_BLOCKS - 1) / G::CHUNK_BLOCKS;
     pl.nt = T > 8 ? 2 : 1;
     const int tpad = 8 * pl.nt;
-    const int sms = num_sms();
+    const int sms = num_sms() * OCC;  // CTA slots
+    const int SMEM_LIMIT = OCC == 2 ? SMEM_LIMIT_2 : dec::SMEM_LIMIT;
+    pl.nw = NW;
+    pl.occ = OCC;
 
     int kw = 1;
     while (kw < NW && static_cast<int64_t>(p.num_tiles) * kw < static_cast<int64_t>(sms) * NW && kw * 2 <= p.nc) kw *= 2;
@@ -292,7 +302,7 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
         const uint32_t xstride = static_cast<uint32_t>(elems * 2 + xpad);
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 127) & ~size_t{127}; return o; };
-        const size_t o_bars = take(8 * (1 + NW * MAX_STAGES));
+        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES));
         const size_t o_x = take(static_cast<size_t>(T) * xstride);
         const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
         const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
@@ -313,16 +323,17 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
 
     // whole K in one slice if it fits next to a >= 2-stage ring; otherwise the largest even slicing
     int cps = p.nc, at = 1, stages = 2;
-    if (layout(cps, 2, 1, false) > SMEM_LIMIT) {
+    if (layout(cps, 2, 1, false) > static_cast<size_t>(SMEM_LIMIT)) {
+        if (!allow_slicing) return false;
         at = 4;
         int slices = 2;
         for (;; ++slices) {
             cps = (p.nc + slices - 1) / slices;
-            if (layout(cps, 2, at, false) <= SMEM_LIMIT) break;
+            if (layout(cps, 2, at, false) <= static_cast<size_t>(SMEM_LIMIT)) break;
             if (cps == 1) return false;
         }
     }
-    while (stages < MAX_STAGES && layout(cps, stages + 1, at, false) <= SMEM_LIMIT) ++stages;
+    while (stages < MAX_STAGES && layout(cps, stages + 1, at, false) <= static_cast<size_t>(SMEM_LIMIT)) ++stages;
     p.cps = cps;
     p.n_slices = (p.nc + cps - 1) / cps;
     p.stages = stages;
@@ -334,14 +345,24 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     return true;
 }
 
-template <int FMT, int NT, int AT>
+// Preference order: two 8-warp CTAs per SM (16 resident warps hide the shared-memory latency of the
+// unpack -> MMA -> scale chains) when the whole problem state fits in half an SM's shared memory,
+// else one CTA per SM with the full 227 KB (activations of many tokens / K-slicing).
+template <int FMT>
+static bool make_plan(const MmArgs& a, int T, Plan& pl) {
+    if (make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
+    return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
+}
+
+template <int FMT, int NT, int AT, int NW, int MINB>
 static int launch_kernel(const Plan& pl, cudaStream_t stream) {
-    auto kern = decode_kernel<FMT, NT, AT>;
+    auto kern = decode_kernel<FMT, NT, AT, NW, MINB>;
     static int configured_dev_mask[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured_dev_mask[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             MINB == 2 ? SMEM_LIMIT_2 : SMEM_LIMIT);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured_dev_mask[dev] = 1;
     }
@@ -360,8 +381,13 @@ static int launch_fmt(const MmArgs& a) {
         Plan pl;
         if (!make_plan<FMT>(s, T, pl)) return GGQ_E_FAMILY;
         int rc;
-        if (pl.nt == 1) rc = pl.at == 1 ? launch_kernel<FMT, 1, 1>(pl, a.stream) : launch_kernel<FMT, 1, 4>(pl, a.stream);
-        else rc = pl.at == 1 ? launch_kernel<FMT, 2, 1>(pl, a.stream) : launch_kernel<FMT, 2, 4>(pl, a.stream);
+        if (pl.occ == 2) {  // AT == 1 by construction
+            rc = pl.nt == 1 ? launch_kernel<FMT, 1, 1, 8, 2>(pl, a.stream) : launch_kernel<FMT, 2, 1, 8, 2>(pl, a.stream);
+        } else if (pl.nt == 1) {
+            rc = pl.at == 1 ? launch_kernel<FMT, 1, 1, 8, 1>(pl, a.stream) : launch_kernel<FMT, 1, 4, 8, 1>(pl, a.stream);
+        } else {
+            rc = pl.at == 1 ? launch_kernel<FMT, 2, 1, 8, 1>(pl, a.stream) : launch_kernel<FMT, 2, 4, 8, 1>(pl, a.stream);
+        }
         if (rc != 0) return rc;
     }
     return 0;
@@ -389,8 +415,8 @@ int decode_plan(int fmt, const MmArgs& a, int* out) {
         case GGQ_Q6_K: ok = dec::make_plan<2>(a, T, pl); break;
     }
     if (!ok) return GGQ_E_FAMILY;
-    const int v[9] = {pl.p.KW, pl.at, pl.nt, pl.p.n_slices, pl.p.cps, pl.p.stages, pl.grid, pl.p.num_batches,
-                      static_cast<int>(pl.smem)};
+    const int v[9] = {pl.p.KW, pl.at, pl.nt, pl.p.n_slices, pl.p.cps, pl.p.stages, pl.grid * 100 + pl.occ,
+                      pl.p.num_batches, static_cast<int>(pl.smem)};
     for (int i = 0; i < 9; ++i) out[i] = v[i];
     return 0;
 }

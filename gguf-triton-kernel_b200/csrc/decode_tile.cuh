@@ -66,14 +66,14 @@ template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B; lanes rea
     static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 608;
     static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 32;
-    static constexpr int SCRATCH_PER_BLOCK = 64;
+    static constexpr int SCRATCH_PER_BLOCK = 80;  // 64 B payload + 16 B pad: rows 20 banks apart
     static constexpr float TBL_MUL = 1.f;
 };
-template <> struct Geo<2> {  // Q6_K: 2 blocks = 512 weights = 420 B (+ up to 12 B of alignment slack)
-    static constexpr int QK = 256, BLK = 210, CHUNK_BLOCKS = 2, CHUNK_ELEMS = 512, CHUNK_BYTES = 420, SLOT = 464;
+template <> struct Geo<2> {  // Q6_K: 2 blocks = 512 weights = 420 B; the 16-byte aligned superset is always 432 B
+    static constexpr int QK = 256, BLK = 210, CHUNK_BLOCKS = 2, CHUNK_ELEMS = 512, CHUNK_BYTES = 420, SLOT = 432;
     static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 16;
-    static constexpr int SCRATCH_PER_BLOCK = 64;
+    static constexpr int SCRATCH_PER_BLOCK = 80;  // 64 B payload + 16 B pad: rows 20 banks apart
     static constexpr float TBL_MUL = -32.f / 16777216.f;    // the -32 of (q6 - 32)
 };
 
@@ -88,8 +88,7 @@ struct StageArgs {
     int nblk;                 // blocks in this sub-step (<= PREP_BLOCKS; even for Q8_0 / Q6_K)
     const uint8_t* xrow[2];   // per n-tile: this lane's activation row (token), at slice-relative k = 0
     int k0;                   // slice-relative element index of the sub-step's first weight
-    const float* tbl;         // [k / GROUP][TPAD] pre-summed activations times Geo::TBL_MUL
-    int tpad;                 // 8 * NT
+    const float* tbl;         // [k / GROUP][8 * NT] pre-summed activations times Geo::TBL_MUL
     uint8_t* scratch;         // this warp's prepared-scale area (SCRATCH_PER_BLOCK * 16 * PREP_BLOCKS)
 };
 
@@ -124,7 +123,9 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint8_t* r1 = r0 + 8 * G::SLOT;
     const uint32_t wrap_sel = (L.t == 3) ? 0x7610u : 0x3210u;
     const int t4 = 4 * L.t;
-    for (int p = 0; p < s.nblk / 2; ++p) {
+#pragma unroll
+    for (int p = 0; p < G::PREP_BLOCKS / 2; ++p) {
+        if (2 * p >= s.nblk) break;
         const uint8_t* a = r0 + 68 * p;
         const uint8_t* b = r1 + 68 * p;
         const uint32_t a0w = ld32(a), a8w = ld32(a + 32), b0w = ld32(b), b8w = ld32(b + 32);
@@ -144,7 +145,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const uint8_t* x = s.xrow[nt] + 2 * kb;
-            const float2 c = ld64f(s.tbl + (kb >> 5) * s.tpad + 8 * nt + 2 * L.t);
+            const float2 c = ld64f(s.tbl + (kb >> 5) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
             uint32_t bf[2];
             bf[0] = ld32(x + 2 * (2 + t4));
@@ -166,7 +167,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const uint8_t* x = s.xrow[nt] + 2 * (kb + 32);
-            const float2 c = ld64f(s.tbl + ((kb >> 5) + 1) * s.tpad + 8 * nt + 2 * L.t);
+            const float2 c = ld64f(s.tbl + ((kb >> 5) + 1) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
             uint2 v = ld64(x + 2 * t4);
             uint32_t bf[2] = {v.x, v.y};
@@ -188,7 +189,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // =============================================================================================
 // prep: lanes decode the 16-byte block headers of the stage (d, dmin, 6-bit scales/mins,
 // q4_k_ref.c:174-186) into fp32, once per (row, block) instead of once per lane:
-//   scratch[(row * PREP_BLOCKS + blk)][c] = float4(d*sc[2c] * 2^24, d*sc[2c+1] * 2^20, dmin*m[2c], dmin*m[2c+1])
+//   scratch[blk * 16 + row][c] = float4(d*sc[2c] * 2^24, d*sc[2c+1] * 2^20, dmin*m[2c], dmin*m[2c+1])
 GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
     using G = Geo<1>;
     for (int p = L.lane; p < 16 * s.nblk; p += 32) {
@@ -199,7 +200,7 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
         const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;
         const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);
         const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
-        float4* out = reinterpret_cast<float4*>(s.scratch + (row * G::PREP_BLOCKS + blk) * 64);
+        float4* out = reinterpret_cast<float4*>(s.scratch + (blk * 16 + row) * G::SCRATCH_PER_BLOCK);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint32_t scw = (c < 2) ? sc_lo : sc_hi, mw = (c < 2) ? m_lo : m_hi;
@@ -235,11 +236,13 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
     const uint8_t* r1 = r0 + 8 * G::SLOT;
     const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < s.nblk; ++i) {
+#pragma unroll
+    for (int i = 0; i < G::PREP_BLOCKS; ++i) {
+        if (i >= s.nblk) break;
         const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
         const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
-        const uint8_t* sc0 = s.scratch + (L.g * G::PREP_BLOCKS + i) * 64;
-        const uint8_t* sc1 = sc0 + 8 * G::PREP_BLOCKS * 64;
+        const uint8_t* sc0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
+        const uint8_t* sc1 = sc0 + 8 * G::SCRATCH_PER_BLOCK;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
@@ -254,8 +257,8 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             for (int nt = 0; nt < NT; ++nt) {
                 const uint4 xe = ld128(s.xrow[nt] + 2 * (kb + 8 * L.t));
                 const uint4 xo = ld128(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t));
-                const float* tb = s.tbl + (kb >> 5) * s.tpad + 8 * nt + 2 * L.t;
-                const float2 se = ld64f(tb), so = ld64f(tb + s.tpad);
+                const float* tb = s.tbl + (kb >> 5) * (8 * NT) + 8 * nt + 2 * L.t;
+                const float2 se = ld64f(tb), so = ld64f(tb + (8 * NT));
                 float de[4], dd[4];
                 uint32_t bf[2] = {xe.x, xe.y};
                 mma16816(de, e1, bf, zero);
@@ -297,25 +300,32 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // =============================================================================================
 // Q6_K
 // =============================================================================================
-// prep: scratch[(row * PREP_BLOCKS + blk)][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh] * 2^24  (fp32, exact)
+// prep: scratch[blk * 16 + row][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh] * 2^24  (fp32, exact)
 GGQ_DEV void prep_q6_k(const Lane& L, const StageArgs& s) {
     using G = Geo<2>;
     for (int p = L.lane; p < 16 * s.nblk; p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
         const float d = h2f(ld16(b + 208)) * 16777216.f;
-        float* out = reinterpret_cast<float*>(s.scratch + (row * G::PREP_BLOCKS + blk) * 64);
+        float sc[16];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {  // scales 2jj, 2jj+1
             const uint32_t two = ld16(b + 192 + 2 * jj);
-            const float s0 = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two & 0xff)));
-            const float s1 = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two >> 8)));
-            // sub-block j = 8h + 2grp + lh  ->  slot (h*2 + lh)*4 + grp
-            const int j0 = 2 * jj;  // lh = 0
-            const int h = j0 >> 3, grp = (j0 >> 1) & 3;
-            out[(h * 2 + 0) * 4 + grp] = s0;
-            out[(h * 2 + 1) * 4 + grp] = s1;
+            sc[2 * jj] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two & 0xff)));
+            sc[2 * jj + 1] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>(two >> 8)));
         }
+        float4* out = reinterpret_cast<float4*>(s.scratch + (blk * 16 + row) * G::SCRATCH_PER_BLOCK);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int lh = 0; lh < 2; ++lh) {  // sub-block j = 8h + 2grp + lh  ->  out[h*2 + lh] = (grp 0..3)
+                float4 v;
+                v.x = sc[8 * h + 0 + lh];
+                v.y = sc[8 * h + 2 + lh];
+                v.z = sc[8 * h + 4 + lh];
+                v.w = sc[8 * h + 6 + lh];
+                out[h * 2 + lh] = v;
+            }
     }
 }
 
@@ -341,8 +351,8 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
     using G = Geo<2>;
     const uint8_t* b0 = r0 + i * G::BLK;
     const uint8_t* b1 = r1 + i * G::BLK;
-    const uint8_t* sc0 = s.scratch + (L.g * G::PREP_BLOCKS + i) * 64;
-    const uint8_t* sc1 = sc0 + 8 * G::PREP_BLOCKS * 64;
+    const uint8_t* sc0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
+    const uint8_t* sc1 = sc0 + 8 * G::SCRATCH_PER_BLOCK;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -365,7 +375,7 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const uint2 xv = ld64(s.xrow[nt] + 2 * kk);
-                    const float2 c = ld64f(s.tbl + j16 * s.tpad + 8 * nt + 2 * L.t);
+                    const float2 c = ld64f(s.tbl + j16 * (8 * NT) + 8 * nt + 2 * L.t);
                     float d[4] = {c.x, c.y, c.x, c.y};
                     const uint32_t bf[2] = {xv.x, xv.y};
                     mma16816(d, fa, bf, d);
@@ -384,7 +394,9 @@ GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     using G = Geo<2>;
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
     const uint8_t* r1 = r0 + 8 * G::SLOT;
-    for (int i = 0; i < s.nblk; i += 2) {  // chunk starts at an even block: even blocks 4-byte aligned
+#pragma unroll
+    for (int i = 0; i < G::PREP_BLOCKS; i += 2) {  // chunk starts at an even block: even blocks 4-byte aligned
+        if (i >= s.nblk) break;
         compute_q6_k_block<NT, false>(L, s, i, r0, r1, acc);
         compute_q6_k_block<NT, true>(L, s, i + 1, r0, r1, acc);
     }

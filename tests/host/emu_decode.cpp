@@ -126,7 +126,6 @@ static int run(int T, int K, unsigned seed) {
             s.rows = stage;
             for (int nt = 0; nt < NT; ++nt) s.xrow[nt] = &X[static_cast<size_t>(std::min(8 * nt + L.g, T - 1)) * xpitch];
             s.tbl = tbl.data();
-            s.tpad = tpad;
             s.scratch = scratch;
             for (int b = 0; b < nblk; b += G::PREP_BLOCKS) {  // same sub-stepping as decode.cu
                 s.data_off = data_off + b * G::BLK;
