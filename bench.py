@@ -216,6 +216,24 @@ def detail_table(torch, ext, hbm_peak):
     return rows
 
 
+def prefill_table(torch, ext, tf_peak):
+    """Secondary numbers: prefill GEMM TFLOP/s per quant type on the BASELINE config 3/4 shapes."""
+    rows = []
+    shapes = [("q4_k", 28672, 8192, 4096), ("q8_0", 28672, 8192, 4096), ("q6_k", 4096, 14336, 2048),
+              ("q6_k", 128256, 4096, 2048)]
+    for fmt, o, k, t in shapes:
+        W = gen_weights(torch, fmt, o, k, "cuda", 11)
+        X = torch.randn((t, k), device="cuda", dtype=torch.float16)
+        C = torch.empty((t, o), device="cuda", dtype=torch.float16)
+        ms = timed(torch, None, lambda: ext.mm(ext.FMT_ID[fmt], W, X, o, t, k, out=C), 5, 3, 1)
+        tf = 2.0 * t * o * k / (ms * 1e-3) / 1e12
+        rows.append({"fmt": fmt, "O": o, "K": k, "T": t, "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+                     "frac_measured_bf16_peak": round(tf / tf_peak, 3), "frac_2250_nominal": round(tf / 2250.0, 3)})
+        del W, X, C
+        torch.cuda.empty_cache()
+    return rows
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -232,7 +250,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     ext.lib()
-    hbm_peak, _, peak_src = peaks()
+    hbm_peak, tf_peak, peak_src = peaks()
 
     rows = O // world
     assert rows * world == O
@@ -317,6 +335,7 @@ def run_ours(args):
     }
     if args.detail:
         out["detail"] = detail_table(torch, ext, hbm_peak)
+        out["prefill"] = prefill_table(torch, ext, tf_peak)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -40,7 +40,7 @@ static int select_family(int fmt, const MmArgs& a) {
     if (a.O < 16) return GGQ_FAMILY_GENERIC;  // less than one 16-row MMA tile: one warp per row is the better fit
     if (a.T <= 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;
     if (a.T >= 64 && prefill_supports(fmt, a)) return GGQ_FAMILY_PREFILL;
-    if (a.T > 16 && a.T < 64 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;  // looped over 16-token groups
+    if (a.T > 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;  // looped over 16-token groups
     return GGQ_FAMILY_GENERIC;
 }
 

@@ -104,6 +104,8 @@ static int launch_dequant_t(const uint8_t* W, void* out, int64_t O, int64_t K, c
 }
 
 int launch_dequant(int fmt, const uint8_t* W, void* out, int64_t O, int64_t K, cudaStream_t s) {
+    int rc = 0;
+    if (launch_dequant64(fmt, W, out, O, K, s, &rc)) return rc;  // same code path as the prefill GEMM's B operand
     switch (fmt) {
         case GGQ_Q8_0: return launch_dequant_t<Q8_0>(W, out, O, K, s);
         case GGQ_Q4_K: return launch_dequant_t<Q4_K>(W, out, O, K, s);

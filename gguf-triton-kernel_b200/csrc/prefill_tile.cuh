@@ -1,0 +1,166 @@
+// prefill_tile.cuh — bit-exact vectorized dequantization of one row x 64 consecutive weights.
+//
+// Used by BOTH the prefill GEMM (source = shared-memory staging units filled by TMA) and the
+// standalone dequantize op ggq_dequant_*_f16 (source = global memory), so the Tier-0 test
+// "dequantized weights are bit-exact" checks exactly the values that are fed to tcgen05.mma.
+//
+// A "unit row" is the 16-byte aligned superset of the blocks of one weight row that cover UNIT_K
+// consecutive weights; `p` points at the unit row, `off` is the byte offset of the first block inside
+// it (0 for Q4_K; 0/8 for Q8_0; 0,2,..,14 for Q6_K — identical for every row of a block column because
+// rows are whole 16-byte vectors).  out[c] holds weights 8c..8c+7 of the 64 as fp16.
+//
+// Recipes (reference: utils/quantize/q8_0.py:94, q4_k.py:137-143,156, q6_k.py:126-135):
+//   Q8_0  RN16(d * q)                      one fp16 multiply
+//   Q4_K  RN16(fma(d*sc, q, -(dmin*m)))    fp32, products exact
+//   Q6_K  RN16((d*sc) * (q6 - 32))         fp32 product exact; written as a multiply (not an FMA against
+//                                          -32*d*sc) so that zeros keep the reference's sign: (-s)*0 = -0
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ggq {
+namespace pre {
+
+template <int FMT> struct Unit;
+template <> struct Unit<0> {  // Q8_0: 4 blocks = 128 weights = 136 B; block column starts at 136c (0 or 8 mod 16)
+    static constexpr int QK = 32, BLK = 34, UNIT_K = 128, UNIT_BYTES = 136, BOX_BYTES = 144;
+};
+template <> struct Unit<1> {  // Q4_K: 1 super-block = 256 weights = 144 B, always 16-byte aligned
+    static constexpr int QK = 256, BLK = 144, UNIT_K = 256, UNIT_BYTES = 144, BOX_BYTES = 144;
+};
+template <> struct Unit<2> {  // Q6_K: 1 super-block = 256 weights = 210 B at 210c (even offsets 0..14 mod 16)
+    static constexpr int QK = 256, BLK = 210, UNIT_K = 256, UNIT_BYTES = 210, BOX_BYTES = 224;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);  // cvt.rn.f16x2.f32
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float hbits2f(uint32_t bits) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(bits)));
+}
+__device__ __forceinline__ float byte2f(uint32_t w, int i) { return static_cast<float>((w >> (8 * i)) & 0xffu); }
+
+// 32-bit load at an address that is only 2-byte aligned (alignment is uniform across the warp)
+__device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t{3});
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    if (sh == 0) return q[0];
+    return __funnelshift_r(q[0], q[1], sh);
+}
+
+// ---- Q8_0 -------------------------------------------------------------------------------------
+// kb: which 64-weight half of the 128-weight unit (blocks 2kb, 2kb+1)
+__device__ __forceinline__ void dequant64(Unit<0>, const uint8_t* p, int off, int kb, uint4 out[8]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p + off + 68 * kb);  // 4-byte aligned; 17 words
+    uint32_t r[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) r[i] = w[i];
+    const uint32_t dA = r[0] & 0xffffu, dB = r[8] >> 16;
+    const __half2 dA2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(dA)));
+    const __half2 dB2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(dB)));
+    const __half2 bias = __float2half2_rn(1152.f);
+    auto cvt = [&](uint32_t q4, const __half2 d2, uint32_t& lo, uint32_t& hi) {
+        const uint32_t u = q4 ^ 0x80808080u;                        // q + 128
+        uint32_t a = __byte_perm(u, 0x64646464u, 0x5140);           // halves 1024 + (q + 128)
+        uint32_t b = __byte_perm(u, 0x64646464u, 0x7362);
+        __half2 ha = __hsub2(*reinterpret_cast<__half2*>(&a), bias);  // exact q
+        __half2 hb = __hsub2(*reinterpret_cast<__half2*>(&b), bias);
+        ha = __hmul2(ha, d2);                                       // RN16(d * q)
+        hb = __hmul2(hb, d2);
+        lo = *reinterpret_cast<uint32_t*>(&ha);
+        hi = *reinterpret_cast<uint32_t*>(&hb);
+    };
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // block A: quants start 2 bytes into word 0
+        const uint32_t v0 = __funnelshift_r(r[2 * c], r[2 * c + 1], 16);
+        const uint32_t v1 = __funnelshift_r(r[2 * c + 1], r[2 * c + 2], 16);
+        cvt(v0, dA2, out[c].x, out[c].y);
+        cvt(v1, dA2, out[c].z, out[c].w);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // block B: quants are word aligned (34 + 2 = 36)
+        cvt(r[9 + 2 * c], dB2, out[4 + c].x, out[4 + c].y);
+        cvt(r[10 + 2 * c], dB2, out[4 + c].z, out[4 + c].w);
+    }
+}
+
+// ---- Q4_K -------------------------------------------------------------------------------------
+// kb: 0..3, the 64-weight chunk of the super-block (sub-blocks 2kb = low nibbles, 2kb+1 = high nibbles)
+__device__ __forceinline__ void dequant64(Unit<1>, const uint8_t* p, int /*off*/, int kb, uint4 out[8]) {
+    const uint4 h = *reinterpret_cast<const uint4*>(p);
+    const float d = hbits2f(h.x & 0xffffu), dmin = hbits2f(h.x >> 16);
+    uint32_t sc0, sc1, m0, m1;
+    if (kb < 2) {  // sub-blocks 0..3: plain 6-bit fields (q4_k_ref.c:176-178)
+        const int s = 16 * kb;
+        sc0 = (h.y >> s) & 63u;
+        sc1 = (h.y >> (s + 8)) & 63u;
+        m0 = (h.z >> s) & 63u;
+        m1 = (h.z >> (s + 8)) & 63u;
+    } else {       // sub-blocks 4..7: low 4 bits in bytes 8..11, high 2 bits in the top of bytes 0..7 (:180-183)
+        const int s = 16 * (kb - 2);
+        sc0 = ((h.w >> s) & 0xFu) | (((h.y >> (s + 6)) & 3u) << 4);
+        sc1 = ((h.w >> (s + 8)) & 0xFu) | (((h.y >> (s + 14)) & 3u) << 4);
+        m0 = ((h.w >> (s + 4)) & 0xFu) | (((h.z >> (s + 6)) & 3u) << 4);
+        m1 = ((h.w >> (s + 12)) & 0xFu) | (((h.z >> (s + 14)) & 3u) << 4);
+    }
+    const float ds0 = d * static_cast<float>(sc0), ds1 = d * static_cast<float>(sc1);        // exact
+    const float dm0 = -(dmin * static_cast<float>(m0)), dm1 = -(dmin * static_cast<float>(m1));
+    const uint4* qs = reinterpret_cast<const uint4*>(p + 16 + 32 * kb);
+    const uint4 qa = qs[0], qb = qs[1];
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t w0 = w[2 * c], w1 = w[2 * c + 1];
+        const uint32_t l0 = w0 & 0x0F0F0F0Fu, l1 = w1 & 0x0F0F0F0Fu;
+        const uint32_t h0 = (w0 >> 4) & 0x0F0F0F0Fu, h1 = (w1 >> 4) & 0x0F0F0F0Fu;
+        out[c].x = pack2(fmaf(ds0, byte2f(l0, 0), dm0), fmaf(ds0, byte2f(l0, 1), dm0));
+        out[c].y = pack2(fmaf(ds0, byte2f(l0, 2), dm0), fmaf(ds0, byte2f(l0, 3), dm0));
+        out[c].z = pack2(fmaf(ds0, byte2f(l1, 0), dm0), fmaf(ds0, byte2f(l1, 1), dm0));
+        out[c].w = pack2(fmaf(ds0, byte2f(l1, 2), dm0), fmaf(ds0, byte2f(l1, 3), dm0));
+        out[4 + c].x = pack2(fmaf(ds1, byte2f(h0, 0), dm1), fmaf(ds1, byte2f(h0, 1), dm1));
+        out[4 + c].y = pack2(fmaf(ds1, byte2f(h0, 2), dm1), fmaf(ds1, byte2f(h0, 3), dm1));
+        out[4 + c].z = pack2(fmaf(ds1, byte2f(h1, 0), dm1), fmaf(ds1, byte2f(h1, 1), dm1));
+        out[4 + c].w = pack2(fmaf(ds1, byte2f(h1, 2), dm1), fmaf(ds1, byte2f(h1, 3), dm1));
+    }
+}
+
+// ---- Q6_K -------------------------------------------------------------------------------------
+// kb: 0..3; half h = kb >> 1, nibble/bit-pair selector gp = kb & 1 (groups g = 2gp, 2gp + 1 of 32 weights):
+//   weight 128h + 32g + l = (ql[64h + 32(g&1) + l] nibble gp) | ((qh[32h + l] >> 2g) & 3) << 4   (q6_k_ref.c:320-336)
+__device__ __forceinline__ void dequant64(Unit<2>, const uint8_t* p, int off, int kb, uint4 out[8]) {
+    const uint8_t* b = p + off;  // 2-byte aligned
+    const int h = kb >> 1, gp = kb & 1;
+    const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
+    const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
+    float ds[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        ds[i] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>((scw >> (8 * i)) & 0xffu)));  // exact
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {  // group g = 2gp + gi
+        const uint8_t* ql = b + 64 * h + 32 * gi;
+        const uint8_t* qh = b + 128 + 32 * h;
+        const int hshift = 4 * gp + 2 * gi;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {  // 8 weights: l = 8*c4 .. 8*c4+7, sub-block 2*gi + (c4 >> 1) of the four
+            const float s = ds[2 * gi + (c4 >> 1)];
+            uint32_t o[4];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const uint32_t lw = ld32_any(ql + 8 * c4 + 4 * v);
+                const uint32_t hw = ld32_any(qh + 8 * c4 + 4 * v);
+                const uint32_t lo = (gp ? (lw >> 4) : lw) & 0x0F0F0F0Fu;
+                const uint32_t hi = ((hw >> hshift) & 0x03030303u) << 4;
+                const uint32_t q = lo | hi;  // four 6-bit quants
+                o[2 * v] = pack2(s * (byte2f(q, 0) - 32.f), s * (byte2f(q, 1) - 32.f));
+                o[2 * v + 1] = pack2(s * (byte2f(q, 2) - 32.f), s * (byte2f(q, 3) - 32.f));
+            }
+            out[4 * gi + c4] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+}  // namespace pre
+}  // namespace ggq

@@ -150,11 +150,47 @@ def test_generic_family(ext, fmt, shape):
     assert fro < 6e-4  # exact fp16 weights, fp32 accumulate: only the fp16 output rounding remains
 
 
+PREFILL_SHAPES = [  # (M = out-features, N = tokens, K)
+    (256, 256, 512), (256, 128, 256), (300, 130, 1024), (512, 64, 2048), (1000, 700, 2048), (200, 1, 512),
+    (768, 512, 4096), (257, 257, 768),
+]
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("shape", PREFILL_SHAPES)
+def test_prefill_family(ext, fmt, shape):
+    M, N, K = shape
+    if fmt == "q6_k":
+        K = max(2048, K // 2048 * 2048)  # rows must be whole 16-byte vectors: K % 2048 == 0
+    A = orc.random_blocks(fmt, M, K, seed=M + N)
+    X = rand_x(N, K, K + 1)
+    C = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_PREFILL)
+    mx, fro = check_tier1(fmt, A, X, M, N, K, C, "prefill")
+    assert fro < 6e-4  # bit-exact fp16 weights, fp32 accumulation in TMEM: only the fp16 output rounding remains
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_prefill_real_packer_weights(ext, fmt):
+    M, N, K = 512, 384, 2048
+    rng = np.random.default_rng(7)
+    W = rng.standard_normal((M, K)).astype(np.float16)
+    X = rand_x(N, K, 8)
+    A = packers.quantize(fmt, W)
+    C = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_PREFILL)
+    check_tier1(fmt, A, X, M, N, K, C, "prefill real")
+    rows = rng.choice(M, 16, replace=False)
+    toks = rng.choice(N, 8, replace=False)
+    rowB = orc.packed_nbytes(fmt, 1, K)
+    Asub = np.concatenate([A[r * rowB:(r + 1) * rowB] for r in rows])
+    Ccpu = orc.mmq_cpu(fmt, Asub, X[toks], len(rows), len(toks), K)
+    assert orc.allclose_ref(Ccpu.astype(np.float32), C[np.ix_(toks, rows)].astype(np.float32), 0.01)
+
+
 @pytest.mark.parametrize("fmt", FMTS)
 def test_auto_dispatch_matches_pinned_families(ext, fmt):
     M, K = 64, 2048
     A = orc.random_blocks(fmt, M, K, seed=11)
-    for N in (1, 16, 20):
+    for N in (1, 16, 20, 64, 200):
         X = rand_x(N, K, N)
         fam = ext.lib().ggq_select_family(ext.FMT_ID[fmt], M, N, K)
         Ca = run_mm(ext, fmt, A, X, M, N, K)
