@@ -259,7 +259,6 @@ def run_ours(args):
     x_host = torch.randn((T, K), dtype=torch.float16).pin_memory()
     x_dev = x_host.to("cuda")
     c_shard = torch.empty((T, rows), device="cuda", dtype=torch.float16)
-    c_full = torch.empty((world, T, rows), device="cuda", dtype=torch.float16) if world > 1 else None
     c_host = torch.empty((T, O), dtype=torch.float16).pin_memory()
 
     # sanity: Tier-1 parity on sampled rows before anything is timed (oracle = checker only)
@@ -276,23 +275,23 @@ def run_ours(args):
         assert mx <= orc.TIER1_MAX and fro <= orc.TIER1_FRO, ("bench parity", mx, fro)
         parity = {"max_over_max": mx, "rel_fro": fro, "rows_sampled": len(pick)}
 
+    layer = None
+    if world > 1:
+        from multigpu import nsplit
+        layer = nsplit.NSplitLinear(FMT, W, O, K, mode=args.exchange, max_tokens=16)
+
     def step_device():
         if world > 1:
-            dist.broadcast(x_dev, src=0)
-        ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard)
-        if world > 1:
-            dist.all_gather_into_tensor(c_full, c_shard)
+            layer.forward(x_dev)          # broadcast X, per-rank GEMV on the shard, exchange -> [T, O] everywhere
+        else:
+            ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard)
 
     def step_e2e():
         x_dev.copy_(x_host, non_blocking=True)
         if world > 1:
-            dist.broadcast(x_dev, src=0)
-        c = mmq_q4_k(W, x_dev, rows, T, K)
-        if world > 1:
-            dist.all_gather_into_tensor(c_full, c)
-            c_host.view(T, world, rows).copy_(c_full.permute(1, 0, 2), non_blocking=True)
+            c_host.copy_(layer.forward(x_dev), non_blocking=True)
         else:
-            c_host.copy_(c, non_blocking=True)
+            c_host.copy_(mmq_q4_k(W, x_dev, rows, T, K), non_blocking=True)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -319,7 +318,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 (fp16 activations x in-register dequantized weights, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": L2_NOTE, "parallelism": f"N-split x{world}" if world > 1 else "single GPU",
+        "config": {"workload": WORKLOAD, "l2": L2_NOTE,
+                   "parallelism": f"N-split x{world}, exchange={args.exchange}" if world > 1 else "single GPU",
                    "fmt": FMT, "O": O, "K": K, "T": T},
         "e2e": {"value": e2e, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": T * K * 2,
                 "d2h_bytes_per_step": T * O * 2},
@@ -348,6 +348,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--detail", action="store_true", help="also sweep quant types / shapes / T (secondary table)")
+    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
+                    help="N>1: how the [T, O/N] slices reach every rank (NCCL all-gather, or peer stores fused into the epilogue)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,0 +1,118 @@
+"""N-split of one quantized layer across G GPUs of one node (one process per GPU).
+
+The reference has no multi-GPU code; this is the BASELINE config-5 layout.  Rows of the packed weight
+are independent units (no block straddles a row: K % QK == 0, kernels/mmq_q4_k.py:263), so rank r
+simply owns the contiguous byte range of rows [r*O/G, (r+1)*O/G).  Activations are replicated
+(broadcast from rank 0), every rank computes C_r[T, O/G] with the single-GPU kernels, and the slices
+are exchanged so that every rank ends up with the full C[T, O].  Two exchange paths:
+
+  "nccl"   ncclAllGather of the contiguous [T, O/G] slices into [G, T, O/G], then (T > 1) one transpose
+           copy to [T, O].  Baseline path.
+  "fused"  no collective kernel at all: the GEMM/GEMV epilogue stores each output tile straight into the
+           [T, O] buffers of ALL ranks through NVLink peer mappings (torch symmetric memory supplies
+           the peer pointers; ggq_mm_ex takes them as n_out outputs with ldc = O), followed by one
+           symmetric-memory barrier.  The transfer overlaps the math tile by tile.
+
+`mm_fn` is injectable so the host logic (sharding arithmetic, exchange layout) is testable on CPU with
+the gloo backend and a stand-in matmul.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+FMT_QK = {"q8_0": 32, "q4_k": 256, "q6_k": 256}
+FMT_BLK = {"q8_0": 34, "q4_k": 144, "q6_k": 210}
+
+
+def row_bytes(fmt: str, K: int) -> int:
+    if K % FMT_QK[fmt]:
+        raise ValueError(f"K={K} is not a multiple of the {fmt} block size")
+    return K // FMT_QK[fmt] * FMT_BLK[fmt]
+
+
+def shard_rows(O: int, world: int, rank: int) -> tuple[int, int]:
+    """Row range of `rank`.  O must divide evenly (true for every BASELINE shape: SURVEY §8e)."""
+    if O % world:
+        raise ValueError(f"O={O} is not divisible by the {world} ranks")
+    per = O // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_packed(fmt: str, A: torch.Tensor, O: int, K: int, world: int, rank: int) -> torch.Tensor:
+    """The byte slice of the flat packed tensor `A` that holds this rank's rows (a view, no copy)."""
+    rb = row_bytes(fmt, K)
+    if A.numel() != O * rb:
+        raise ValueError("packed size does not match O, K")
+    lo, hi = shard_rows(O, world, rank)
+    return A[lo * rb:hi * rb]
+
+
+def assemble(gathered: torch.Tensor) -> torch.Tensor:
+    """[G, T, O/G] (all-gather order) -> [T, O] contiguous."""
+    G, T, per = gathered.shape
+    if T == 1:
+        return gathered.reshape(1, G * per)
+    return gathered.permute(1, 0, 2).reshape(T, G * per)
+
+
+class NSplitLinear:
+    def __init__(self, fmt: str, A_shard: torch.Tensor, O: int, K: int, *, group=None, mode: str = "nccl",
+                 max_tokens: int = 16, mm_fn: Callable | None = None):
+        self.fmt, self.O, self.K = fmt, O, K
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.lo, self.hi = shard_rows(O, self.world, self.rank)
+        self.per = self.hi - self.lo
+        if A_shard.numel() != self.per * row_bytes(fmt, K):
+            raise ValueError("A_shard does not hold exactly this rank's rows")
+        self.A = A_shard
+        self.mode = mode
+        self.max_tokens = max_tokens
+        self.mm_fn = mm_fn
+        self._symm = None
+        if mm_fn is None:
+            from kernels import _ext  # the CUDA library; raises if it is not built (no fallback)
+            self._ext = _ext
+            self._fmt_id = _ext.FMT_ID[fmt]
+        if mode == "fused":
+            self._init_symm()
+        elif mode != "nccl":
+            raise ValueError(mode)
+
+    # ---- fused path: peer-mapped output buffers ----
+    def _init_symm(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = self.A.device
+        self._out = symm_mem.empty((self.max_tokens, self.O), dtype=torch.float16, device=dev)
+        self._symm = symm_mem.rendezvous(self._out, self.group)
+        col_off = self.lo * 2  # bytes: this rank's column offset inside every rank's [T, O] buffer
+        self._peer_ptrs = [int(p) + col_off for p in self._symm.buffer_ptrs]
+        # own buffer first (purely cosmetic: all are written)
+        self._peer_ptrs = [self._peer_ptrs[self.rank]] + [p for i, p in enumerate(self._peer_ptrs) if i != self.rank]
+
+    def forward(self, X: torch.Tensor, *, broadcast: bool = True) -> torch.Tensor:
+        """X: fp16 [T, K] (valid on rank 0 when `broadcast`).  Returns C[T, O] on every rank."""
+        T = X.shape[0]
+        if broadcast and self.world > 1:
+            dist.broadcast(X, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
+                           group=self.group)
+        if self.mode == "fused":
+            if T > self.max_tokens:
+                raise ValueError(f"T={T} exceeds max_tokens={self.max_tokens} of the symmetric buffer")
+            self._symm.barrier(channel=0)   # every rank has finished reading the previous result
+            self._ext.mm_ex(self._fmt_id, self.A, X, self._peer_ptrs, self.O, self.per, T, self.K)
+            self._symm.barrier(channel=1)   # every rank's tiles have landed everywhere
+            return self._out[:T]
+        if self.mm_fn is not None:
+            c = self.mm_fn(self.A, X, self.per, T, self.K)
+        else:
+            c = self._ext.mm(self._fmt_id, self.A, X, self.per, T, self.K)
+        if self.world == 1:
+            return c
+        gathered = torch.empty((self.world * T, self.per), dtype=c.dtype, device=c.device)
+        dist.all_gather_into_tensor(gathered, c.contiguous(), group=self.group)  # rank-major concatenation
+        return assemble(gathered.view(self.world, T, self.per))
