@@ -25,6 +25,7 @@
 #include "decode_tile.cuh"
 #include "formats.cuh"
 #include "ptx.cuh"
+#include "tma.cuh"
 
 namespace ggq {
 namespace dec {
@@ -53,7 +54,8 @@ struct Params {
 
 // NW warps per CTA, MINB CTAs per SM (register budget), NT 8-token n-tiles, AT live tiles per warp
 template <int FMT, int NT, int AT, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) decode_kernel(const Params p) {
+__global__ void __launch_bounds__(NW * 32, MINB)
+decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     using G = Geo<FMT>;
     constexpr int STAGE_BYTES = 16 * G::SLOT;
     constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) decode_kernel(const Params p) {
     uint64_t* my_full = bars + 1 + w * STG;
 
     if (tid == 0) {
+        prefetch_tmap(&map_w);
         mbar_init(&bars[0], 1);
         for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);
         fence_mbar_init();
@@ -103,22 +106,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) decode_kernel(const Params p) {
         const int64_t row0 = tile_of(c.batch, c.a) * 16;
         const int chunk = c.slice * p.cps + c.ci;
         const int b0 = chunk * G::CHUNK_BLOCKS;
-        const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
         const int goff = b0 * G::BLK;
-        const int src = goff & ~15;
-        const int len = ((goff + nblk * G::BLK + 15) & ~15) - src;
-        const int64_t left = p.O - row0;
-        const int nrows = left < 16 ? static_cast<int>(left) : 16;
         uint64_t* bar = my_full + stage;
-        if (lane == 0) {  // one lane issues the whole stage: UBLKCP is a per-warp (uniform datapath) instruction
-            mbar_arrive_expect_tx(bar, static_cast<uint32_t>(len * nrows));
-            uint8_t* dst = ring + stage * STAGE_BYTES;
-            const uint8_t* from = p.W + row0 * p.rowB + src;
-            for (int r = 0; r < nrows; ++r) {
-                bulk_g2s(dst, from, static_cast<uint32_t>(len), bar);
-                dst += G::SLOT;
-                from += p.rowB;
-            }
+        if (lane == 0) {  // one 2-D TMA tile per stage: 16 rows x SLOT bytes of the raw packed rows, starting at the
+                          // 16-byte aligned superset of the chunk; rows >= O and bytes past the row end are zero-filled
+            mbar_arrive_expect_tx(bar, STAGE_BYTES);
+            tma_load_2d(ring + stage * STAGE_BYTES, &map_w, (goff & ~15) >> 2, static_cast<int>(row0), bar);
         }
     };
 
@@ -158,25 +151,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) decode_kernel(const Params p) {
                 }
                 mbar_wait(&bars[0], x_phase);
                 x_phase ^= 1;
-                const int ngrp = ne / G::GROUP;
-                for (int idx = tid; idx < ngrp * TPAD; idx += NW * 32) {
-                    const int j = idx / TPAD, col = idx % TPAD;
-                    float sum = 0.f;
-                    if (col < p.T) {
-                        const uint4* src = reinterpret_cast<const uint4*>(xs + col * p.x_stride + j * G::GROUP * 2);
-#pragma unroll
-                        for (int v = 0; v < G::GROUP / 8; ++v) {
-                            const uint4 q = src[v];
-                            const uint32_t r[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                sum += h2f(r[h] & 0xffffu);
-                                sum += h2f(r[h] >> 16);
-                            }
-                        }
-                    }
-                    tbl[idx] = sum * G::TBL_MUL;
-                }
+                stage_activations<FMT, NT>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
                 __syncthreads();
             }
 #pragma unroll
@@ -366,7 +341,13 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         configured_dev_mask[dev] = 1;
     }
-    kern<<<pl.grid, NW * 32, pl.smem, stream>>>(pl.p);
+    // the packed rows viewed as int32 [O, rowB / 4]; box = 16 rows x SLOT bytes
+    alignas(64) CUtensorMap map_w;
+    if (!make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_INT32, pl.p.W, static_cast<uint64_t>(pl.p.rowB / 4),
+                     static_cast<uint64_t>(pl.p.O), static_cast<uint64_t>(pl.p.rowB), Geo<FMT>::SLOT / 4, 16,
+                     CU_TENSOR_MAP_SWIZZLE_NONE))
+        return static_cast<int>(cudaErrorInvalidValue);
+    kern<<<pl.grid, NW * 32, pl.smem, stream>>>(map_w, pl.p);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -33,6 +33,14 @@ namespace dec {
 GGQ_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 GGQ_DEV uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 GGQ_DEV float h2f(uint32_t bits) { return __half2float(__ushort_as_half(static_cast<unsigned short>(bits))); }
+GGQ_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
+GGQ_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
+GGQ_DEV void mma16816_bf16(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[4]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
 // D = A(16x16, row) * B(16x8, col) + C, fp16 inputs, fp32 accumulate (HMMA.16816.F32 on sm_100a)
 GGQ_DEV void mma16816(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[4]) {
     asm volatile(
@@ -57,13 +65,14 @@ namespace dec {
 template <int FMT> struct Geo;
 template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B; lanes read 32-bit words: slot/4 % 32 == 12
     static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = 16, CHUNK_ELEMS = 512, CHUNK_BYTES = 544, SLOT = 560;
+    // SLOT is also the inner extent of the TMA box: 544 B of chunk + 16 B of the next one (keeps the pitch conflict free)
     static constexpr int PREP_BLOCKS = 16;      // blocks handled per prep/compute sub-step of a stage
     static constexpr int GROUP = 32;            // activations per pre-summed group (one block)
     static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
     static constexpr float TBL_MUL = -128.f / 16777216.f;   // cancels the +128 of (q ^ 0x80)
 };
-template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B; lanes read 64-bit: slot % 128 == 96
-    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 608;
+template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B = the TMA box (dense pitch: 2-way conflict on 64-bit loads)
+    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 576;
     static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 32;
     static constexpr int SCRATCH_PER_BLOCK = 80;  // 64 B payload + 16 B pad: rows 20 banks apart
@@ -98,6 +107,7 @@ GGQ_DEV uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p
 GGQ_DEV float4 ld128f(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 GGQ_DEV float2 ld64f(const float* p) { return *reinterpret_cast<const float2*>(p); }
 GGQ_DEV uint32_t ld16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+GGQ_DEV float ldf(const uint8_t* p) { return *reinterpret_cast<const float*>(p); }
 
 // acc[0,1] belong to row g, acc[2,3] to row g+8 (mma C fragment order)
 template <int NT> struct Acc {
@@ -187,47 +197,94 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // =============================================================================================
 // Q4_K
 // =============================================================================================
-// prep: lanes decode the 16-byte block headers of the stage (d, dmin, 6-bit scales/mins,
-// q4_k_ref.c:174-186) into fp32, once per (row, block) instead of once per lane:
-//   scratch[blk * 16 + row][c] = float4(d*sc[2c] * 2^24, d*sc[2c+1] * 2^20, dmin*m[2c], dmin*m[2c+1])
+// Q4_K specifics of this family:
+//  * activations are stored PERMUTED inside every group of four (x0 x2 x1 x3), so the nibble masks
+//    (w & 0x000F000F -> weights l, l+2;  (w >> 8) & 0x000F000F -> l+1, l+3) need no byte shuffle;
+//  * the -dmin*m_j*sum_j(x) term of all 8 sub-blocks of a block is ONE extra bf16 MMA per block:
+//    A = the 6-bit mins m_j (exact in bf16), B = the 32-activation sums split into bf16 hi + lo
+//    (k slots 0..7 = hi_j, 8..15 = lo_j; ~2^-17 relative), then acc -= dmin * D;
+//  * prep decodes each 16-byte block header once per (row, block) into an 80-byte scratch entry:
+//      float s[8]  = d*sc_j * 2^24 (even j: low nibbles = q*2^-24) / * 2^20 (odd j: high nibbles = q*2^-20)
+//      u32  mp[4]  = bf16x2(m_2t, m_2t+1)        float dmin
+GGQ_DEV uint32_t bf16_bits_rn(float f) {  // float -> bf16 bit pattern, round to nearest even (finite inputs)
+    uint32_t u = f2u(f);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return u >> 16;
+}
+
 GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
     using G = Geo<1>;
     for (int p = L.lane; p < 16 * s.nblk; p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
         const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
+        const float d24 = d * 16777216.f, d20 = d * 1048576.f;
         const uint32_t u0 = h.y, u1 = h.z, u2 = h.w;
-        const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;
-        const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);
+        const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;  // sub-blocks 0..3 (q4_k_ref.c:176-178)
+        const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);         // 4..7 (:180-183)
         const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
-        float4* out = reinterpret_cast<float4*>(s.scratch + (blk * 16 + row) * G::SCRATCH_PER_BLOCK);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t scw = (c < 2) ? sc_lo : sc_hi, mw = (c < 2) ? m_lo : m_hi;
-            const int sh = 16 * (c & 1);
-            const float s_e = d * static_cast<float>((scw >> sh) & 0xff);
-            const float s_o = d * static_cast<float>((scw >> (sh + 8)) & 0xff);
-            const float m_e = dmin * static_cast<float>((mw >> sh) & 0xff);
-            const float m_o = dmin * static_cast<float>((mw >> (sh + 8)) & 0xff);
-            float4 v;
-            v.x = s_e * 16777216.f;  // low nibbles enter the MMA as q * 2^-24
-            v.y = s_o * 1048576.f;   // high nibbles as q * 2^-20
-            v.z = m_e;
-            v.w = m_o;
-            out[c] = v;
-        }
+        uint8_t* e = s.scratch + (blk * 16 + row) * G::SCRATCH_PER_BLOCK;
+        float4 a, b;
+        a.x = d24 * static_cast<float>(sc_lo & 0xff);
+        a.y = d20 * static_cast<float>((sc_lo >> 8) & 0xff);
+        a.z = d24 * static_cast<float>((sc_lo >> 16) & 0xff);
+        a.w = d20 * static_cast<float>(sc_lo >> 24);
+        b.x = d24 * static_cast<float>(sc_hi & 0xff);
+        b.y = d20 * static_cast<float>((sc_hi >> 8) & 0xff);
+        b.z = d24 * static_cast<float>((sc_hi >> 16) & 0xff);
+        b.w = d20 * static_cast<float>(sc_hi >> 24);
+        uint4 m;  // integers < 64 are exact in bf16: bits = float bits >> 16
+        m.x = (f2u(static_cast<float>(m_lo & 0xff)) >> 16) | (f2u(static_cast<float>((m_lo >> 8) & 0xff)) & 0xffff0000u);
+        m.y = (f2u(static_cast<float>((m_lo >> 16) & 0xff)) >> 16) | (f2u(static_cast<float>(m_lo >> 24)) & 0xffff0000u);
+        m.z = (f2u(static_cast<float>(m_hi & 0xff)) >> 16) | (f2u(static_cast<float>((m_hi >> 8) & 0xff)) & 0xffff0000u);
+        m.w = (f2u(static_cast<float>((m_hi >> 16) & 0xff)) >> 16) | (f2u(static_cast<float>(m_hi >> 24)) & 0xffff0000u);
+        *reinterpret_cast<float4*>(e) = a;
+        *reinterpret_cast<float4*>(e + 16) = b;
+        *reinterpret_cast<uint4*>(e + 32) = m;
+        *reinterpret_cast<float*>(e + 48) = dmin;
     }
 }
 
-// One 32-bit word = 4 bytes = 4 low nibbles (sub-block 2c) + 4 high nibbles (sub-block 2c+1).
-// Swapping bytes 1 and 2 first makes each fp16 pair hold two CONSECUTIVE weights.
-GGQ_DEV void q4_to_h2(uint32_t w, uint32_t& lo01, uint32_t& lo23, uint32_t& hi01, uint32_t& hi23) {
-    const uint32_t p = prmt(w, w, 0x3120);
-    const uint32_t p8 = p >> 8;
-    lo01 = p & 0x000F000Fu;    // q * 2^-24 (fp16 subnormals)
-    lo23 = p8 & 0x000F000Fu;
-    hi01 = p & 0x00F000F0u;    // q * 2^-20
-    hi23 = p8 & 0x00F000F0u;
+// Per (block, token) the staging pass turns the raw activations into what compute_q4_k reads:
+// the permuted fp16 row (in place) and the bf16 hi/lo split of the eight 32-activation sums, laid out
+// as the B fragment of the min-term MMA: xb[(blk * TPAD + token) * 4 + t] = {bf16x2(hi_2t, hi_2t+1),
+// bf16x2(lo_2t, lo_2t+1)}.  `x` points at the 256 activations of the block (16-byte aligned).
+GGQ_DEV void q4k_stage_block(uint8_t* x, uint2* xb_entry /* 4 entries */, bool token_valid) {
+    if (!token_valid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) xb_entry[t] = uint2{0u, 0u};
+        return;
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float sum = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            uint4* ptr = reinterpret_cast<uint4*>(x + 64 * j + 16 * v);
+            const uint4 q = *ptr;
+            sum += h2f(q.x & 0xffffu);
+            sum += h2f(q.x >> 16);
+            sum += h2f(q.y & 0xffffu);
+            sum += h2f(q.y >> 16);
+            sum += h2f(q.z & 0xffffu);
+            sum += h2f(q.z >> 16);
+            sum += h2f(q.w & 0xffffu);
+            sum += h2f(q.w >> 16);
+            uint4 o;  // (x0 x1 x2 x3) -> (x0 x2 x1 x3), per group of four
+            o.x = prmt(q.x, q.y, 0x5410);
+            o.y = prmt(q.x, q.y, 0x7632);
+            o.z = prmt(q.z, q.w, 0x5410);
+            o.w = prmt(q.z, q.w, 0x7632);
+            *ptr = o;
+        }
+        const uint32_t h = f2u(sum) & 0xffff0000u;          // bf16 hi part (truncated), exact remainder below
+        hi[j] = h >> 16;
+        lo[j] = bf16_bits_rn(sum - u2f(h));
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        xb_entry[t] = uint2{hi[2 * t] | (hi[2 * t + 1] << 16), lo[2 * t] | (lo[2 * t + 1] << 16)};
 }
 
 template <int NT>
@@ -236,58 +293,72 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
     const uint8_t* r1 = r0 + 8 * G::SLOT;
     const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint2* xbt = reinterpret_cast<const uint2*>(s.tbl);
 #pragma unroll
     for (int i = 0; i < G::PREP_BLOCKS; ++i) {
         if (i >= s.nblk) break;
         const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
         const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
-        const uint8_t* sc0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
-        const uint8_t* sc1 = sc0 + 8 * G::SCRATCH_PER_BLOCK;
+        const uint8_t* e0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
+        const uint8_t* e1 = e0 + 8 * G::SCRATCH_PER_BLOCK;
+        const float4 sa0 = ld128f(e0), sa1 = ld128f(e0 + 16), sb0 = ld128f(e1), sb1 = ld128f(e1 + 16);
+        const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
+        const float sb[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
+        {   // ---- min term of the whole block: one bf16 MMA per n-tile
+            const uint32_t mpa = ld32(e0 + 32 + 4 * L.t), mpb = ld32(e1 + 32 + 4 * L.t);
+            const float dmin_a = ldf(e0 + 48), dmin_b = ldf(e1 + 48);
+            const uint32_t ma[4] = {mpa, mpb, mpa, mpb};
+            const int blk = (s.k0 >> 8) + i;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint2 xb = xbt[(blk * (8 * NT) + 8 * nt + L.g) * 4 + L.t];
+                const uint32_t bfr[2] = {xb.x, xb.y};
+                float dm[4];
+                mma16816_bf16(dm, ma, bfr, zero);
+                acc.v[nt][0] = fmaf(-dmin_a, dm[0], acc.v[nt][0]);
+                acc.v[nt][1] = fmaf(-dmin_a, dm[1], acc.v[nt][1]);
+                acc.v[nt][2] = fmaf(-dmin_b, dm[2], acc.v[nt][2]);
+                acc.v[nt][3] = fmaf(-dmin_b, dm[3], acc.v[nt][3]);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
-            const float4 sa = ld128f(sc0 + 16 * c), sb = ld128f(sc1 + 16 * c);
-            uint32_t e1[4], e2[4], o1[4], o2[4];  // A fragments: even/odd sub-block, first/second k16 step
-            q4_to_h2(wa.x, e1[0], e1[2], o1[0], o1[2]);
-            q4_to_h2(wb.x, e1[1], e1[3], o1[1], o1[3]);
-            q4_to_h2(wa.y, e2[0], e2[2], o2[0], o2[2]);
-            q4_to_h2(wb.y, e2[1], e2[3], o2[1], o2[3]);
+            uint32_t e1f[4], e2f[4], o1f[4], o2f[4];  // A fragments: even/odd sub-block, first/second k16 step
+            e1f[0] = wa.x & 0x000F000Fu;  e1f[2] = (wa.x >> 8) & 0x000F000Fu;   // q * 2^-24 (fp16 subnormals)
+            o1f[0] = wa.x & 0x00F000F0u;  o1f[2] = (wa.x >> 8) & 0x00F000F0u;   // q * 2^-20
+            e1f[1] = wb.x & 0x000F000Fu;  e1f[3] = (wb.x >> 8) & 0x000F000Fu;
+            o1f[1] = wb.x & 0x00F000F0u;  o1f[3] = (wb.x >> 8) & 0x00F000F0u;
+            e2f[0] = wa.y & 0x000F000Fu;  e2f[2] = (wa.y >> 8) & 0x000F000Fu;
+            o2f[0] = wa.y & 0x00F000F0u;  o2f[2] = (wa.y >> 8) & 0x00F000F0u;
+            e2f[1] = wb.y & 0x000F000Fu;  e2f[3] = (wb.y >> 8) & 0x000F000Fu;
+            o2f[1] = wb.y & 0x00F000F0u;  o2f[3] = (wb.y >> 8) & 0x00F000F0u;
             const int kb = s.k0 + 256 * i + 64 * c;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint4 xe = ld128(s.xrow[nt] + 2 * (kb + 8 * L.t));
+                const uint4 xe = ld128(s.xrow[nt] + 2 * (kb + 8 * L.t));        // permuted: (x0 x2 | x1 x3 | x4 x6 | x5 x7)
                 const uint4 xo = ld128(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t));
-                const float* tb = s.tbl + (kb >> 5) * (8 * NT) + 8 * nt + 2 * L.t;
-                const float2 se = ld64f(tb), so = ld64f(tb + (8 * NT));
                 float de[4], dd[4];
                 uint32_t bf[2] = {xe.x, xe.y};
-                mma16816(de, e1, bf, zero);
+                mma16816(de, e1f, bf, zero);
                 bf[0] = xe.z;
                 bf[1] = xe.w;
-                mma16816(de, e2, bf, de);
+                mma16816(de, e2f, bf, de);
                 bf[0] = xo.x;
                 bf[1] = xo.y;
-                mma16816(dd, o1, bf, zero);
+                mma16816(dd, o1f, bf, zero);
                 bf[0] = xo.z;
                 bf[1] = xo.w;
-                mma16816(dd, o2, bf, dd);
+                mma16816(dd, o2f, bf, dd);
                 float a0 = acc.v[nt][0], a1 = acc.v[nt][1], a2 = acc.v[nt][2], a3 = acc.v[nt][3];
-                a0 = fmaf(sa.x, de[0], a0);
-                a1 = fmaf(sa.x, de[1], a1);
-                a2 = fmaf(sb.x, de[2], a2);
-                a3 = fmaf(sb.x, de[3], a3);
-                a0 = fmaf(sa.y, dd[0], a0);
-                a1 = fmaf(sa.y, dd[1], a1);
-                a2 = fmaf(sb.y, dd[2], a2);
-                a3 = fmaf(sb.y, dd[3], a3);
-                a0 = fmaf(-sa.z, se.x, a0);
-                a1 = fmaf(-sa.z, se.y, a1);
-                a2 = fmaf(-sb.z, se.x, a2);
-                a3 = fmaf(-sb.z, se.y, a3);
-                a0 = fmaf(-sa.w, so.x, a0);
-                a1 = fmaf(-sa.w, so.y, a1);
-                a2 = fmaf(-sb.w, so.x, a2);
-                a3 = fmaf(-sb.w, so.y, a3);
+                a0 = fmaf(sa[2 * c], de[0], a0);
+                a1 = fmaf(sa[2 * c], de[1], a1);
+                a2 = fmaf(sb[2 * c], de[2], a2);
+                a3 = fmaf(sb[2 * c], de[3], a3);
+                a0 = fmaf(sa[2 * c + 1], dd[0], a0);
+                a1 = fmaf(sa[2 * c + 1], dd[1], a1);
+                a2 = fmaf(sb[2 * c + 1], dd[2], a2);
+                a3 = fmaf(sb[2 * c + 1], dd[3], a3);
                 acc.v[nt][0] = a0;
                 acc.v[nt][1] = a1;
                 acc.v[nt][2] = a2;
@@ -399,6 +470,47 @@ GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
         if (i >= s.nblk) break;
         compute_q6_k_block<NT, false>(L, s, i, r0, r1, acc);
         compute_q6_k_block<NT, true>(L, s, i + 1, r0, r1, acc);
+    }
+}
+
+// ---- activation staging pass (after the TMA copies of the K-slice have landed) ------------------
+// Builds the per-slice table every thread block needs next to the raw fp16 rows:
+//   Q8_0 / Q6_K: tbl[j][col] = TBL_MUL * sum of the GROUP activations of group j of token col (fp32)
+//   Q4_K:        the bf16 hi/lo B fragments of the min-term MMA, and permutes the rows in place
+// `ne` activations per token row (multiple of 256 for Q4_K), rows `x_stride` bytes apart.
+template <int FMT, int NT>
+GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int ne, int T, int tid, int nthreads) {
+    using G = Geo<FMT>;
+    constexpr int TPAD = 8 * NT;
+    if (FMT == 1) {
+        uint2* xb = reinterpret_cast<uint2*>(tbl);
+        const int nblk = ne / 256;
+        for (int idx = tid; idx < nblk * TPAD; idx += nthreads) {
+            const int b = idx / TPAD, col = idx % TPAD;
+            q4k_stage_block(xs + (col < T ? col : 0) * x_stride + b * 512, xb + (b * TPAD + col) * 4, col < T);
+        }
+    } else {
+        const int ngrp = ne / G::GROUP;
+        for (int idx = tid; idx < ngrp * TPAD; idx += nthreads) {
+            const int j = idx / TPAD, col = idx % TPAD;
+            float sum = 0.f;
+            if (col < T) {
+                const uint8_t* src = xs + col * x_stride + j * G::GROUP * 2;
+#pragma unroll
+                for (int v = 0; v < G::GROUP / 8; ++v) {
+                    const uint4 q = ld128(src + 16 * v);
+                    sum += h2f(q.x & 0xffffu);
+                    sum += h2f(q.x >> 16);
+                    sum += h2f(q.y & 0xffffu);
+                    sum += h2f(q.y >> 16);
+                    sum += h2f(q.z & 0xffffu);
+                    sum += h2f(q.z >> 16);
+                    sum += h2f(q.w & 0xffffu);
+                    sum += h2f(q.w >> 16);
+                }
+            }
+            tbl[idx] = sum * G::TBL_MUL;
+        }
     }
 }
 

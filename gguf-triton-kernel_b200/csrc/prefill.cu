@@ -18,17 +18,14 @@
 // w_full[u] (TMA tx) -> dequant -> w_empty[u] (4 warps); acc_full (tcgen05.commit) -> epilogue.
 // Roofline: 2*T*O*K FLOP on the fp16 tensor pipe; packed weights are read T/256 times (L2-resident
 // across the token tiles that run concurrently), X is read O/256 times.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
 #include <algorithm>
-#include <mutex>
 
 #include "../../include/ggq.h"
 #include "common.cuh"
 #include "formats.cuh"
 #include "prefill_tile.cuh"
 #include "ptx.cuh"
+#include "tma.cuh"
 
 namespace ggq {
 namespace pre {
@@ -55,16 +52,6 @@ template <int FMT> constexpr int smem_bytes() {
 }
 
 // ---- tcgen05 / TMA wrappers -------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                  : "memory");
@@ -290,31 +277,6 @@ prefill_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled get_encode() {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
-    });
-    return fn;
-}
-
-static bool make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
-    auto enc = get_encode();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {inner, outer};
-    const cuuint64_t strides[1] = {row_stride_bytes};
-    const cuuint32_t box[2] = {box_inner, box_outer};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int FMT>
 static int launch_t(const MmArgs& a) {
     using U = Unit<FMT>;

@@ -38,6 +38,9 @@ inline float h2f(uint32_t bits) {
     return sign ? -v : v;
 }
 
+inline uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
 struct WarpEmu {
     std::barrier<> bar{32};
     uint32_t a[32][4];
@@ -64,6 +67,26 @@ inline void mma16816(float d[4], const uint32_t a[4], const uint32_t b[2], const
             const float av = frag_half(w.a[(row & 7) * 4 + ta][(row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0)], k & 1);
             const float bv = frag_half(w.b[col * 4 + ta][k >= 8 ? 1 : 0], k & 1);
             acc += av * bv;  // products of fp16 values are exact in fp32
+        }
+        d[i] = acc;
+    }
+    w.bar.arrive_and_wait();
+}
+inline float frag_bf16(uint32_t reg, int hi) { return u2f((hi ? (reg >> 16) : (reg & 0xffff)) << 16); }
+inline void mma16816_bf16(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[4]) {
+    WarpEmu& w = *tls_warp;
+    const int lane = tls_lane, g = lane >> 2, t = lane & 3;
+    std::memcpy(w.a[lane], a, 16);
+    std::memcpy(w.b[lane], b, 8);
+    const float cin[4] = {c[0], c[1], c[2], c[3]};
+    w.bar.arrive_and_wait();
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + ((i & 2) ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = cin[i];
+        for (int k = 0; k < 16; ++k) {
+            const int ta = (k & 7) >> 1;
+            acc += frag_bf16(w.a[(row & 7) * 4 + ta][(row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0)], k & 1) *
+                   frag_bf16(w.b[col * 4 + ta][k >= 8 ? 1 : 0], k & 1);
         }
         d[i] = acc;
     }

@@ -82,7 +82,10 @@ static int run(int T, int K, unsigned seed) {
         }
     // activations: T rows of fp16, row pitch K + 8 halves (any 16-byte multiple works)
     const int xpitch = (K + 8) * 2;
-    std::vector<uint8_t> X(static_cast<size_t>(T) * xpitch + 64, 0);
+    alignas(16) static uint8_t Xbuf[16 * (8192 + 8) * 2 + 64];
+    if (K > 8192) return 2;
+    struct XV { uint8_t* p; uint8_t* data() { return p; } uint8_t& operator[](size_t i) { return p[i]; } } X{Xbuf};
+    std::memset(Xbuf, 0, sizeof(Xbuf));
     std::vector<double> xd(static_cast<size_t>(T) * K);
     for (int t = 0; t < T; ++t)
         for (int k = 0; k < K; ++k) {
@@ -90,15 +93,10 @@ static int run(int T, int K, unsigned seed) {
             std::memcpy(&X[static_cast<size_t>(t) * xpitch + 2 * k], &h, 2);
             xd[static_cast<size_t>(t) * K + k] = h2f(h);
         }
-    // pre-summed activation table, as the kernel builds it
+    // per-slice activation table (and, for Q4_K, the in-place permutation) exactly as the kernel builds it
     const int tpad = 8 * NT, ngrp = K / G::GROUP;
-    std::vector<float> tbl(static_cast<size_t>(ngrp) * tpad, 0.f);
-    for (int j = 0; j < ngrp; ++j)
-        for (int t = 0; t < T; ++t) {
-            float sum = 0.f;
-            for (int k = 0; k < G::GROUP; ++k) sum += static_cast<float>(xd[static_cast<size_t>(t) * K + j * G::GROUP + k]);
-            tbl[static_cast<size_t>(j) * tpad + t] = sum * G::TBL_MUL;
-        }
+    std::vector<float> tbl(static_cast<size_t>(ngrp) * tpad + 64, 0.f);
+    stage_activations<FMT, NT>(X.data(), static_cast<uint32_t>(xpitch), tbl.data(), K, T, 0, 1);
     // emulate the staging of every chunk and run the warp
     alignas(16) static uint8_t stage[16 * 1024];
     alignas(16) static uint8_t scratch[16 * 8 * 64 + 64];
