@@ -19,6 +19,7 @@
 //       activations of all tokens do not fit in shared memory at once, else 1)
 // HBM traffic = packed weight bytes once (+ <= 3 % activations/outputs); roofline: HBM bandwidth.
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/ggq.h"
 #include "common.cuh"
@@ -48,6 +49,7 @@ struct Params {
     int n_slices;
     int num_batches;
     int stages;
+    int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
     uint32_t x_stride;  // bytes between token rows in shared memory
     uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red;
 };
@@ -57,9 +59,9 @@ template <int FMT, int NT, int AT, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     using G = Geo<FMT>;
-    constexpr int STAGE_BYTES = 16 * G::SLOT;
+    constexpr int SUBTILES = G::CHUNK_BLOCKS / G::PREP_BLOCKS;  // TMA boxes per stage
+    constexpr int STAGE_BYTES = SUBTILES * 16 * G::SLOT;
     constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
-    constexpr int TPAD = 8 * NT;
     extern __shared__ __align__(128) uint8_t smem[];
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -108,10 +110,13 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         const int b0 = chunk * G::CHUNK_BLOCKS;
         const int goff = b0 * G::BLK;
         uint64_t* bar = my_full + stage;
-        if (lane == 0) {  // one 2-D TMA tile per stage: 16 rows x SLOT bytes of the raw packed rows, starting at the
-                          // 16-byte aligned superset of the chunk; rows >= O and bytes past the row end are zero-filled
+        if (lane == 0) {  // 2-D TMA boxes of 16 rows x SLOT bytes of the raw packed rows, each starting at the 16-byte
+                          // aligned superset of its blocks; rows >= O and bytes past the row end are zero-filled
             mbar_arrive_expect_tx(bar, STAGE_BYTES);
-            tma_load_2d(ring + stage * STAGE_BYTES, &map_w, (goff & ~15) >> 2, static_cast<int>(row0), bar);
+#pragma unroll
+            for (int sub = 0; sub < SUBTILES; ++sub)
+                tma_load_2d(ring + stage * STAGE_BYTES + sub * 16 * G::SLOT, &map_w,
+                            ((goff + sub * G::PREP_BLOCKS * G::BLK) & ~15) >> 2, static_cast<int>(row0), bar);
         }
     };
 
@@ -163,13 +168,15 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
                     const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
                     StageArgs s;
-                    s.rows = ring + cstage * STAGE_BYTES;
                     s.xrow[0] = xs + tok0 * p.x_stride;
                     s.xrow[1] = xs + tok1 * p.x_stride;
+                    s.xv[0] = L.g < p.T;
+                    s.xv[1] = 8 + L.g < p.T;
                     s.tbl = tbl;
                     s.scratch = scr;
-                    for (int b = 0; b < nblk; b += G::PREP_BLOCKS) {
-                        s.data_off = ((b0 * G::BLK) & 15) + b * G::BLK;
+                    for (int b = 0; b < nblk && !p.dbg_skip_compute; b += G::PREP_BLOCKS) {
+                        s.rows = ring + cstage * STAGE_BYTES + (b / G::PREP_BLOCKS) * 16 * G::SLOT;
+                        s.data_off = (b0 * G::BLK) & 15;
                         s.nblk = min(G::PREP_BLOCKS, nblk - b);
                         s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
                         Tile<FMT, NT>::prep(L, s);
@@ -263,13 +270,19 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     const int SMEM_LIMIT = OCC == 2 ? SMEM_LIMIT_2 : dec::SMEM_LIMIT;
     pl.nw = NW;
     pl.occ = OCC;
+    {
+        static const int skip = [] { const char* e = getenv("GGQ_DECODE_NOCOMPUTE"); return (e && e[0] == '1') ? 1 : 0; }();
+        p.dbg_skip_compute = skip;
+    }
 
     int kw = 1;
-    while (kw < NW && static_cast<int64_t>(p.num_tiles) * kw < static_cast<int64_t>(sms) * NW && kw * 2 <= p.nc) kw *= 2;
+    while (kw * 2 <= NW && NW % (kw * 2) == 0 && static_cast<int64_t>(p.num_tiles) * kw < static_cast<int64_t>(sms) * NW &&
+           kw * 2 <= p.nc)
+        kw *= 2;
     p.KW = kw;
     const int wt = NW / kw;
 
-    constexpr int STAGE_BYTES = 16 * G::SLOT;
+    constexpr int STAGE_BYTES = (G::CHUNK_BLOCKS / G::PREP_BLOCKS) * 16 * G::SLOT;
     constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
     const uint32_t xpad = (FMT == 1) ? 64u : 32u;  // x row pitch = 64 (128-bit loads) / 32 (64-bit loads) mod 128
     auto layout = [&](int cps, int stages, int at, bool commit) -> size_t {
@@ -326,6 +339,7 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
 template <int FMT>
 static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     if (make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
+    if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 2) return true;
     return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
 }
 
@@ -364,6 +378,8 @@ static int launch_fmt(const MmArgs& a) {
         int rc;
         if (pl.occ == 2) {  // AT == 1 by construction
             rc = pl.nt == 1 ? launch_kernel<FMT, 1, 1, 8, 2>(pl, a.stream) : launch_kernel<FMT, 2, 1, 8, 2>(pl, a.stream);
+        } else if (pl.nw == 12) {
+            rc = pl.nt == 1 ? launch_kernel<FMT, 1, 1, 12, 1>(pl, a.stream) : launch_kernel<FMT, 2, 1, 12, 1>(pl, a.stream);
         } else if (pl.nt == 1) {
             rc = pl.at == 1 ? launch_kernel<FMT, 1, 1, 8, 1>(pl, a.stream) : launch_kernel<FMT, 1, 4, 8, 1>(pl, a.stream);
         } else {

@@ -59,20 +59,23 @@ namespace ggq {
 namespace dec {
 
 // ---- per-format staging geometry -------------------------------------------------------------
-// CHUNK_BLOCKS blocks of one row form the unit a pipeline stage holds for each of the 16 rows.
+// CHUNK_BLOCKS blocks of one row form the unit a pipeline stage holds for each of the 16 rows; a stage is
+// CHUNK_BLOCKS / PREP_BLOCKS sub-tiles of [16 rows x SLOT bytes], each filled by one 2-D TMA box.
 // SLOT is the shared-memory pitch between the 16 rows of a stage; it is >= the largest copy
 // (chunk bytes + 16-byte alignment slack) and chosen so the per-lane loads below are bank-conflict free.
 template <int FMT> struct Geo;
-template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B; lanes read 32-bit words: slot/4 % 32 == 12
+template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B in one TMA box of 560 B (16 B of the next chunk ride along so
+                             // that slot/4 % 32 == 12 and the lanes' 32-bit loads are conflict free; measured faster than
+                             // two 272 B boxes: TMA cost is per box row)
     static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = 16, CHUNK_ELEMS = 512, CHUNK_BYTES = 544, SLOT = 560;
-    // SLOT is also the inner extent of the TMA box: 544 B of chunk + 16 B of the next one (keeps the pitch conflict free)
-    static constexpr int PREP_BLOCKS = 16;      // blocks handled per prep/compute sub-step of a stage
+    static constexpr int PREP_BLOCKS = 16;      // blocks handled per prep/compute sub-step (= one TMA box) of a stage
     static constexpr int GROUP = 32;            // activations per pre-summed group (one block)
     static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
     static constexpr float TBL_MUL = -128.f / 16777216.f;   // cancels the +128 of (q ^ 0x80)
 };
-template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B = the TMA box (dense pitch: 2-way conflict on 64-bit loads)
-    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 576;
+template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B, two TMA boxes of 2 blocks (288 B pitch: rows land 8 banks
+                             // apart, so the lanes' 64-bit loads are conflict free)
+    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 288;
     static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 32;
     static constexpr int SCRATCH_PER_BLOCK = 80;  // 64 B payload + 16 B pad: rows 20 banks apart
@@ -96,12 +99,18 @@ struct StageArgs {
     int data_off;             // byte offset of this sub-step's first block inside every slot
     int nblk;                 // blocks in this sub-step (<= PREP_BLOCKS; even for Q8_0 / Q6_K)
     const uint8_t* xrow[2];   // per n-tile: this lane's activation row (token), at slice-relative k = 0
+    bool xv[2];               // per n-tile: does this lane's token exist?  Loads of missing tokens are predicated
+                              // off (their MMA columns are never stored), which also keeps the shared-memory
+                              // wavefront count proportional to T instead of 8
     int k0;                   // slice-relative element index of the sub-step's first weight
     const float* tbl;         // [k / GROUP][8 * NT] pre-summed activations times Geo::TBL_MUL
     uint8_t* scratch;         // this warp's prepared-scale area (SCRATCH_PER_BLOCK * 16 * PREP_BLOCKS)
 };
 
 GGQ_DEV uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+GGQ_DEV uint32_t ld32p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint32_t*>(p) : 0u; }
+GGQ_DEV uint2 ld64p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint2*>(p) : uint2{0u, 0u}; }
+GGQ_DEV uint4 ld128p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint4*>(p) : uint4{0u, 0u, 0u, 0u}; }
 GGQ_DEV uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
 GGQ_DEV uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 GGQ_DEV float4 ld128f(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
@@ -158,11 +167,11 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const float2 c = ld64f(s.tbl + (kb >> 5) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
             uint32_t bf[2];
-            bf[0] = ld32(x + 2 * (2 + t4));
-            bf[1] = ld32(x + 2 * (4 + t4));
+            bf[0] = ld32p(x + 2 * (2 + t4), s.xv[nt]);
+            bf[1] = ld32p(x + 2 * (4 + t4), s.xv[nt]);
             mma16816(d, fa, bf, d);
-            bf[0] = ld32(x + 2 * (18 + t4));
-            bf[1] = ld32(x + 2 * ((20 + t4) & 31));
+            bf[0] = ld32p(x + 2 * (18 + t4), s.xv[nt]);
+            bf[1] = ld32p(x + 2 * ((20 + t4) & 31), s.xv[nt]);
             mma16816(d, fb, bf, d);
             acc.v[nt][0] = fmaf(da_e, d[0], acc.v[nt][0]);
             acc.v[nt][1] = fmaf(da_e, d[1], acc.v[nt][1]);
@@ -179,10 +188,10 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const uint8_t* x = s.xrow[nt] + 2 * (kb + 32);
             const float2 c = ld64f(s.tbl + ((kb >> 5) + 1) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
-            uint2 v = ld64(x + 2 * t4);
+            uint2 v = ld64p(x + 2 * t4, s.xv[nt]);
             uint32_t bf[2] = {v.x, v.y};
             mma16816(d, fa, bf, d);
-            v = ld64(x + 2 * (16 + t4));
+            v = ld64p(x + 2 * (16 + t4), s.xv[nt]);
             bf[0] = v.x;
             bf[1] = v.y;
             mma16816(d, fb, bf, d);
@@ -218,26 +227,34 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
         const int row = p & 15, blk = p >> 4;
         const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
         const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
-        const float d24 = d * 16777216.f, d20 = d * 1048576.f;
         const uint32_t u0 = h.y, u1 = h.z, u2 = h.w;
         const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;  // sub-blocks 0..3 (q4_k_ref.c:176-178)
         const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);         // 4..7 (:180-183)
         const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
+        // byte -> fp32 without the integer pipe: PRMT builds the bit pattern of 2^23 + n, one FMA removes the 2^23
+        // and applies the scale: (2^23 + n) * c - 2^23 * c == n * c exactly (n * c has <= 17 significant bits)
+        const float d24 = d * 16777216.f, d20 = d * 1048576.f;
+        const float n24 = d24 * -8388608.f, n20 = d20 * -8388608.f;
         uint8_t* e = s.scratch + (blk * 16 + row) * G::SCRATCH_PER_BLOCK;
         float4 a, b;
-        a.x = d24 * static_cast<float>(sc_lo & 0xff);
-        a.y = d20 * static_cast<float>((sc_lo >> 8) & 0xff);
-        a.z = d24 * static_cast<float>((sc_lo >> 16) & 0xff);
-        a.w = d20 * static_cast<float>(sc_lo >> 24);
-        b.x = d24 * static_cast<float>(sc_hi & 0xff);
-        b.y = d20 * static_cast<float>((sc_hi >> 8) & 0xff);
-        b.z = d24 * static_cast<float>((sc_hi >> 16) & 0xff);
-        b.w = d20 * static_cast<float>(sc_hi >> 24);
-        uint4 m;  // integers < 64 are exact in bf16: bits = float bits >> 16
-        m.x = (f2u(static_cast<float>(m_lo & 0xff)) >> 16) | (f2u(static_cast<float>((m_lo >> 8) & 0xff)) & 0xffff0000u);
-        m.y = (f2u(static_cast<float>((m_lo >> 16) & 0xff)) >> 16) | (f2u(static_cast<float>(m_lo >> 24)) & 0xffff0000u);
-        m.z = (f2u(static_cast<float>(m_hi & 0xff)) >> 16) | (f2u(static_cast<float>((m_hi >> 8) & 0xff)) & 0xffff0000u);
-        m.w = (f2u(static_cast<float>((m_hi >> 16) & 0xff)) >> 16) | (f2u(static_cast<float>(m_hi >> 24)) & 0xffff0000u);
+        a.x = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7650)), d24, n24);
+        a.y = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7651)), d20, n20);
+        a.z = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7652)), d24, n24);
+        a.w = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7653)), d20, n20);
+        b.x = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7650)), d24, n24);
+        b.y = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7651)), d20, n20);
+        b.z = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7652)), d24, n24);
+        b.w = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7653)), d20, n20);
+        // mins as bf16 pairs: float(n) = (2^23 + n) - 2^23; integers < 64 are exact in bf16 = the upper halves
+        const float f0 = u2f(prmt(m_lo, 0x4B000000u, 0x7650)) - 8388608.f, f1 = u2f(prmt(m_lo, 0x4B000000u, 0x7651)) - 8388608.f;
+        const float f2 = u2f(prmt(m_lo, 0x4B000000u, 0x7652)) - 8388608.f, f3 = u2f(prmt(m_lo, 0x4B000000u, 0x7653)) - 8388608.f;
+        const float f4 = u2f(prmt(m_hi, 0x4B000000u, 0x7650)) - 8388608.f, f5 = u2f(prmt(m_hi, 0x4B000000u, 0x7651)) - 8388608.f;
+        const float f6 = u2f(prmt(m_hi, 0x4B000000u, 0x7652)) - 8388608.f, f7 = u2f(prmt(m_hi, 0x4B000000u, 0x7653)) - 8388608.f;
+        uint4 m;
+        m.x = prmt(f2u(f0), f2u(f1), 0x7632);
+        m.y = prmt(f2u(f2), f2u(f3), 0x7632);
+        m.z = prmt(f2u(f4), f2u(f5), 0x7632);
+        m.w = prmt(f2u(f6), f2u(f7), 0x7632);
         *reinterpret_cast<float4*>(e) = a;
         *reinterpret_cast<float4*>(e + 16) = b;
         *reinterpret_cast<uint4*>(e + 32) = m;
@@ -311,7 +328,7 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const int blk = (s.k0 >> 8) + i;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint2 xb = xbt[(blk * (8 * NT) + 8 * nt + L.g) * 4 + L.t];
+                const uint2 xb = ld64p(reinterpret_cast<const uint8_t*>(xbt + (blk * (8 * NT) + 8 * nt + L.g) * 4 + L.t), s.xv[nt]);
                 const uint32_t bfr[2] = {xb.x, xb.y};
                 float dm[4];
                 mma16816_bf16(dm, ma, bfr, zero);
@@ -336,8 +353,8 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const int kb = s.k0 + 256 * i + 64 * c;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint4 xe = ld128(s.xrow[nt] + 2 * (kb + 8 * L.t));        // permuted: (x0 x2 | x1 x3 | x4 x6 | x5 x7)
-                const uint4 xo = ld128(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t));
+                const uint4 xe = ld128p(s.xrow[nt] + 2 * (kb + 8 * L.t), s.xv[nt]);   // permuted: (x0 x2 | x1 x3 | x4 x6 | x5 x7)
+                const uint4 xo = ld128p(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t), s.xv[nt]);
                 float de[4], dd[4];
                 uint32_t bf[2] = {xe.x, xe.y};
                 mma16816(de, e1f, bf, zero);
@@ -445,7 +462,7 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
                 const int j16 = (s.k0 + 256 * i) / 16 + 8 * h + 2 * grp + lh;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const uint2 xv = ld64(s.xrow[nt] + 2 * kk);
+                    const uint2 xv = ld64p(s.xrow[nt] + 2 * kk, s.xv[nt]);
                     const float2 c = ld64f(s.tbl + j16 * (8 * NT) + 8 * nt + 2 * L.t);
                     float d[4] = {c.x, c.y, c.x, c.y};
                     const uint32_t bf[2] = {xv.x, xv.y};

@@ -112,21 +112,25 @@ static int run(int T, int K, unsigned seed) {
             const int b0 = c * G::CHUNK_BLOCKS;
             const int nblk = std::min(G::CHUNK_BLOCKS, nb - b0);
             const int goff = b0 * G::BLK;       // byte offset inside a (16-byte aligned) row
-            const int data_off = goff & 15;
-            if (lane < 16) {                    // what the 16 bulk copies of a stage do
-                const int src = goff - data_off;
-                const int len = ((goff + nblk * G::BLK + 15) & ~15) - src;
-                if (len > G::SLOT) { std::fprintf(stderr, "slot overflow %d\n", len); std::exit(3); }
-                std::memcpy(stage + lane * G::SLOT, &W[static_cast<size_t>(lane) * rowB + src], len);
+            constexpr int SUBTILES = G::CHUNK_BLOCKS / G::PREP_BLOCKS;
+            if (lane < 16) {                    // what the TMA boxes of a stage do (zero fill past the row end)
+                for (int sub = 0; sub < SUBTILES; ++sub) {
+                    const int src = (goff + sub * G::PREP_BLOCKS * G::BLK) & ~15;
+                    uint8_t* dst = stage + sub * 16 * G::SLOT + lane * G::SLOT;
+                    for (int i = 0; i < G::SLOT; ++i) dst[i] = (src + i < rowB) ? W[static_cast<size_t>(lane) * rowB + src + i] : 0;
+                }
             }
             syncwarp();
             StageArgs s{};
-            s.rows = stage;
-            for (int nt = 0; nt < NT; ++nt) s.xrow[nt] = &X[static_cast<size_t>(std::min(8 * nt + L.g, T - 1)) * xpitch];
+            for (int nt = 0; nt < NT; ++nt) {
+                s.xrow[nt] = &X[static_cast<size_t>(std::min(8 * nt + L.g, T - 1)) * xpitch];
+                s.xv[nt] = 8 * nt + L.g < T;
+            }
             s.tbl = tbl.data();
             s.scratch = scratch;
             for (int b = 0; b < nblk; b += G::PREP_BLOCKS) {  // same sub-stepping as decode.cu
-                s.data_off = data_off + b * G::BLK;
+                s.rows = stage + (b / G::PREP_BLOCKS) * 16 * G::SLOT;
+                s.data_off = goff & 15;
                 s.nblk = std::min(G::PREP_BLOCKS, nblk - b);
                 s.k0 = (b0 + b) * G::QK;
                 Tile<FMT, NT>::prep(L, s);
