@@ -303,6 +303,20 @@ def run_ours(args):
     ms = timed(torch, dist, step_device, args.steps, args.warmup, world)
     launches = (ext.launch_count() - l0) - args.warmup  # launches inside the timed region, this rank
     ms_e2e = timed(torch, dist, step_e2e, args.steps, args.warmup, world)
+    # the same end-to-end step (pinned H2D of X, mmq_q4_k through the public entry point, D2H of C) captured once
+    # into a CUDA graph and replayed: what a serving loop does to take the Python/launch cost off the critical path
+    ms_e2e_graph = None
+    if world == 1:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step_e2e()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            step_e2e()
+        ms_e2e_graph = timed(torch, dist, g.replay, args.steps, args.warmup, world)
     # kernel alone (no collectives), for the roofline of the dominant kernel
     ms_k = timed(torch, dist, lambda: ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard), args.steps, args.warmup, world)
     clocks = sampler.stop() if sampler else None
@@ -325,13 +339,17 @@ def run_ours(args):
                    "parallelism": f"N-split x{world}, exchange={args.exchange}" if world > 1 else "single GPU",
                    "fmt": FMT, "O": O, "K": K, "T": T},
         "e2e": {"value": e2e, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": T * K * 2,
-                "d2h_bytes_per_step": T * O * 2},
+                "d2h_bytes_per_step": T * O * 2, "mode": "eager Python call per step",
+                "cuda_graph_replay": None if ms_e2e_graph is None else
+                {"value": total_bytes / (ms_e2e_graph * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e_graph}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ggq::dec::decode_kernel<Q4_K,NT=1,AT=1>", "achieved": achieved,
                      "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "us_per_launch": ms_k * 1e3,
-                     "algorithmic_bytes_per_launch": k_bytes, "traffic": None},
+                     "algorithmic_bytes_per_launch": k_bytes,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/, N=1 only)
+                     "traffic": 295552512 + 4535296 if world == 1 else None},
         "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_rows} of {O} rows, one pass ({cpu_dt:.1f} s), numpy oracle port of kernels/cpu_impls"},
         "parity": parity,
