@@ -50,16 +50,14 @@ __device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
     return __funnelshift_r(q[0], q[1], sh);
 }
 
+// All three are templated on HALF: 2 = all 64 weights into out[0..7]; 0 / 1 = only the first / second 32
+// weights into out[0..3] (the 2-CTA prefill kernel splits a row's k-block over two threads).
+
 // ---- Q8_0 -------------------------------------------------------------------------------------
 // kb: which 64-weight half of the 128-weight unit (blocks 2kb, 2kb+1)
-__device__ __forceinline__ void dequant64(Unit<0>, const uint8_t* p, int off, int kb, uint4 out[8]) {
+template <int HALF>
+__device__ __forceinline__ void dequant_q8_0(const uint8_t* p, int off, int kb, uint4* out) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p + off + 68 * kb);  // 4-byte aligned; 17 words
-    uint32_t r[17];
-#pragma unroll
-    for (int i = 0; i < 17; ++i) r[i] = w[i];
-    const uint32_t dA = r[0] & 0xffffu, dB = r[8] >> 16;
-    const __half2 dA2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(dA)));
-    const __half2 dB2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(dB)));
     const __half2 bias = __float2half2_rn(1152.f);
     auto cvt = [&](uint32_t q4, const __half2 d2, uint32_t& lo, uint32_t& hi) {
         const uint32_t u = q4 ^ 0x80808080u;                        // q + 128
@@ -72,64 +70,75 @@ __device__ __forceinline__ void dequant64(Unit<0>, const uint8_t* p, int off, in
         lo = *reinterpret_cast<uint32_t*>(&ha);
         hi = *reinterpret_cast<uint32_t*>(&hb);
     };
+    if (HALF != 1) {  // block A: quants start 2 bytes into word 0
+        uint32_t r[9];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {  // block A: quants start 2 bytes into word 0
-        const uint32_t v0 = __funnelshift_r(r[2 * c], r[2 * c + 1], 16);
-        const uint32_t v1 = __funnelshift_r(r[2 * c + 1], r[2 * c + 2], 16);
-        cvt(v0, dA2, out[c].x, out[c].y);
-        cvt(v1, dA2, out[c].z, out[c].w);
+        for (int i = 0; i < 9; ++i) r[i] = w[i];
+        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(r[0] & 0xffffu)));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t v0 = __funnelshift_r(r[2 * c], r[2 * c + 1], 16);
+            const uint32_t v1 = __funnelshift_r(r[2 * c + 1], r[2 * c + 2], 16);
+            cvt(v0, d2, out[c].x, out[c].y);
+            cvt(v1, d2, out[c].z, out[c].w);
+        }
     }
+    if (HALF != 0) {  // block B: quants are word aligned (34 + 2 = 36)
+        uint4* o = out + (HALF == 2 ? 4 : 0);
+        uint32_t r[9];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {  // block B: quants are word aligned (34 + 2 = 36)
-        cvt(r[9 + 2 * c], dB2, out[4 + c].x, out[4 + c].y);
-        cvt(r[10 + 2 * c], dB2, out[4 + c].z, out[4 + c].w);
+        for (int i = 0; i < 9; ++i) r[i] = w[8 + i];
+        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(r[0] >> 16)));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            cvt(r[1 + 2 * c], d2, o[c].x, o[c].y);
+            cvt(r[2 + 2 * c], d2, o[c].z, o[c].w);
+        }
     }
 }
 
 // ---- Q4_K -------------------------------------------------------------------------------------
 // kb: 0..3, the 64-weight chunk of the super-block (sub-blocks 2kb = low nibbles, 2kb+1 = high nibbles)
-__device__ __forceinline__ void dequant64(Unit<1>, const uint8_t* p, int /*off*/, int kb, uint4 out[8]) {
+template <int HALF>
+__device__ __forceinline__ void dequant_q4_k(const uint8_t* p, int kb, uint4* out) {
     const uint4 h = *reinterpret_cast<const uint4*>(p);
     const float d = hbits2f(h.x & 0xffffu), dmin = hbits2f(h.x >> 16);
-    uint32_t sc0, sc1, m0, m1;
-    if (kb < 2) {  // sub-blocks 0..3: plain 6-bit fields (q4_k_ref.c:176-178)
-        const int s = 16 * kb;
-        sc0 = (h.y >> s) & 63u;
-        sc1 = (h.y >> (s + 8)) & 63u;
-        m0 = (h.z >> s) & 63u;
-        m1 = (h.z >> (s + 8)) & 63u;
-    } else {       // sub-blocks 4..7: low 4 bits in bytes 8..11, high 2 bits in the top of bytes 0..7 (:180-183)
-        const int s = 16 * (kb - 2);
-        sc0 = ((h.w >> s) & 0xFu) | (((h.y >> (s + 6)) & 3u) << 4);
-        sc1 = ((h.w >> (s + 8)) & 0xFu) | (((h.y >> (s + 14)) & 3u) << 4);
-        m0 = ((h.w >> (s + 4)) & 0xFu) | (((h.z >> (s + 6)) & 3u) << 4);
-        m1 = ((h.w >> (s + 12)) & 0xFu) | (((h.z >> (s + 14)) & 3u) << 4);
-    }
-    const float ds0 = d * static_cast<float>(sc0), ds1 = d * static_cast<float>(sc1);        // exact
-    const float dm0 = -(dmin * static_cast<float>(m0)), dm1 = -(dmin * static_cast<float>(m1));
     const uint4* qs = reinterpret_cast<const uint4*>(p + 16 + 32 * kb);
     const uint4 qa = qs[0], qb = qs[1];
     const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint32_t w0 = w[2 * c], w1 = w[2 * c + 1];
-        const uint32_t l0 = w0 & 0x0F0F0F0Fu, l1 = w1 & 0x0F0F0F0Fu;
-        const uint32_t h0 = (w0 >> 4) & 0x0F0F0F0Fu, h1 = (w1 >> 4) & 0x0F0F0F0Fu;
-        out[c].x = pack2(fmaf(ds0, byte2f(l0, 0), dm0), fmaf(ds0, byte2f(l0, 1), dm0));
-        out[c].y = pack2(fmaf(ds0, byte2f(l0, 2), dm0), fmaf(ds0, byte2f(l0, 3), dm0));
-        out[c].z = pack2(fmaf(ds0, byte2f(l1, 0), dm0), fmaf(ds0, byte2f(l1, 1), dm0));
-        out[c].w = pack2(fmaf(ds0, byte2f(l1, 2), dm0), fmaf(ds0, byte2f(l1, 3), dm0));
-        out[4 + c].x = pack2(fmaf(ds1, byte2f(h0, 0), dm1), fmaf(ds1, byte2f(h0, 1), dm1));
-        out[4 + c].y = pack2(fmaf(ds1, byte2f(h0, 2), dm1), fmaf(ds1, byte2f(h0, 3), dm1));
-        out[4 + c].z = pack2(fmaf(ds1, byte2f(h1, 0), dm1), fmaf(ds1, byte2f(h1, 1), dm1));
-        out[4 + c].w = pack2(fmaf(ds1, byte2f(h1, 2), dm1), fmaf(ds1, byte2f(h1, 3), dm1));
+    for (int hf = 0; hf < 2; ++hf) {
+        if (HALF != 2 && HALF != hf) continue;
+        uint32_t sc, m;
+        if (kb < 2) {  // sub-blocks 0..3: plain 6-bit fields (q4_k_ref.c:176-178)
+            const int s = 16 * kb + 8 * hf;
+            sc = (h.y >> s) & 63u;
+            m = (h.z >> s) & 63u;
+        } else {       // sub-blocks 4..7: low 4 bits in bytes 8..11, high 2 bits in the top of bytes 0..7 (:180-183)
+            const int s = 16 * (kb - 2) + 8 * hf;
+            sc = ((h.w >> s) & 0xFu) | (((h.y >> (s + 6)) & 3u) << 4);
+            m = ((h.w >> (s + 4)) & 0xFu) | (((h.z >> (s + 6)) & 3u) << 4);
+        }
+        const float ds = d * static_cast<float>(sc);      // exact
+        const float dm = -(dmin * static_cast<float>(m));  // exact
+        uint4* o = out + ((HALF == 2 && hf == 1) ? 4 : 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t q0 = (hf ? (w[2 * c] >> 4) : w[2 * c]) & 0x0F0F0F0Fu;
+            const uint32_t q1 = (hf ? (w[2 * c + 1] >> 4) : w[2 * c + 1]) & 0x0F0F0F0Fu;
+            o[c].x = pack2(fmaf(ds, byte2f(q0, 0), dm), fmaf(ds, byte2f(q0, 1), dm));
+            o[c].y = pack2(fmaf(ds, byte2f(q0, 2), dm), fmaf(ds, byte2f(q0, 3), dm));
+            o[c].z = pack2(fmaf(ds, byte2f(q1, 0), dm), fmaf(ds, byte2f(q1, 1), dm));
+            o[c].w = pack2(fmaf(ds, byte2f(q1, 2), dm), fmaf(ds, byte2f(q1, 3), dm));
+        }
     }
 }
 
 // ---- Q6_K -------------------------------------------------------------------------------------
 // kb: 0..3; half h = kb >> 1, nibble/bit-pair selector gp = kb & 1 (groups g = 2gp, 2gp + 1 of 32 weights):
 //   weight 128h + 32g + l = (ql[64h + 32(g&1) + l] nibble gp) | ((qh[32h + l] >> 2g) & 3) << 4   (q6_k_ref.c:320-336)
-__device__ __forceinline__ void dequant64(Unit<2>, const uint8_t* p, int off, int kb, uint4 out[8]) {
+template <int HALF>
+__device__ __forceinline__ void dequant_q6_k(const uint8_t* p, int off, int kb, uint4* out) {
     const uint8_t* b = p + off;  // 2-byte aligned
     const int h = kb >> 1, gp = kb & 1;
     const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
@@ -140,13 +149,15 @@ __device__ __forceinline__ void dequant64(Unit<2>, const uint8_t* p, int off, in
         ds[i] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>((scw >> (8 * i)) & 0xffu)));  // exact
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {  // group g = 2gp + gi
+        if (HALF != 2 && HALF != gi) continue;
         const uint8_t* ql = b + 64 * h + 32 * gi;
         const uint8_t* qh = b + 128 + 32 * h;
         const int hshift = 4 * gp + 2 * gi;
+        uint4* o = out + ((HALF == 2 && gi == 1) ? 4 : 0);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {  // 8 weights: l = 8*c4 .. 8*c4+7, sub-block 2*gi + (c4 >> 1) of the four
             const float s = ds[2 * gi + (c4 >> 1)];
-            uint32_t o[4];
+            uint32_t r[4];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
                 const uint32_t lw = ld32_any(ql + 8 * c4 + 4 * v);
@@ -154,12 +165,25 @@ __device__ __forceinline__ void dequant64(Unit<2>, const uint8_t* p, int off, in
                 const uint32_t lo = (gp ? (lw >> 4) : lw) & 0x0F0F0F0Fu;
                 const uint32_t hi = ((hw >> hshift) & 0x03030303u) << 4;
                 const uint32_t q = lo | hi;  // four 6-bit quants
-                o[2 * v] = pack2(s * (byte2f(q, 0) - 32.f), s * (byte2f(q, 1) - 32.f));
-                o[2 * v + 1] = pack2(s * (byte2f(q, 2) - 32.f), s * (byte2f(q, 3) - 32.f));
+                r[2 * v] = pack2(s * (byte2f(q, 0) - 32.f), s * (byte2f(q, 1) - 32.f));
+                r[2 * v + 1] = pack2(s * (byte2f(q, 2) - 32.f), s * (byte2f(q, 3) - 32.f));
             }
-            out[4 * gi + c4] = make_uint4(o[0], o[1], o[2], o[3]);
+            o[c4] = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
+}
+
+template <int HALF> __device__ __forceinline__ void dequant_part(Unit<0>, const uint8_t* p, int off, int kb, uint4* out) {
+    dequant_q8_0<HALF>(p, off, kb, out);
+}
+template <int HALF> __device__ __forceinline__ void dequant_part(Unit<1>, const uint8_t* p, int, int kb, uint4* out) {
+    dequant_q4_k<HALF>(p, kb, out);
+}
+template <int HALF> __device__ __forceinline__ void dequant_part(Unit<2>, const uint8_t* p, int off, int kb, uint4* out) {
+    dequant_q6_k<HALF>(p, off, kb, out);
+}
+template <class U> __device__ __forceinline__ void dequant64(U u, const uint8_t* p, int off, int kb, uint4 out[8]) {
+    dequant_part<2>(u, p, off, kb, out);
 }
 
 }  // namespace pre
