@@ -41,6 +41,34 @@ __device__ __forceinline__ float hbits2f(uint32_t bits) {
 }
 __device__ __forceinline__ float byte2f(uint32_t w, int i) { return static_cast<float>((w >> (8 * i)) & 0xffu); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 process two floats per instruction) ----------------
+struct f2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_bits(f2 v) {
+    return (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+}
+__device__ __forceinline__ f2 bits_f2(unsigned long long b) {
+    return f2{__uint_as_float(static_cast<uint32_t>(b)), __uint_as_float(static_cast<uint32_t>(b >> 32))};
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+// bytes i, i+1 of w as the floats 2^23 + byte (one PRMT each, no integer->float conversion)
+__device__ __forceinline__ f2 magic2(uint32_t w, int i) {
+    return f2{__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + i)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651 + i))};
+}
+
 // 32-bit load at an address that is only 2-byte aligned (alignment is uniform across the warp)
 __device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -121,15 +149,19 @@ __device__ __forceinline__ void dequant_q4_k(const uint8_t* p, int kb, uint4* ou
         }
         const float ds = d * static_cast<float>(sc);      // exact
         const float dm = -(dmin * static_cast<float>(m));  // exact
+        const f2 ds2{ds, ds}, dm2{dm, dm}, m23{-8388608.f, -8388608.f};
         uint4* o = out + ((HALF == 2 && hf == 1) ? 4 : 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint32_t q0 = (hf ? (w[2 * c] >> 4) : w[2 * c]) & 0x0F0F0F0Fu;
             const uint32_t q1 = (hf ? (w[2 * c + 1] >> 4) : w[2 * c + 1]) & 0x0F0F0F0Fu;
-            o[c].x = pack2(fmaf(ds, byte2f(q0, 0), dm), fmaf(ds, byte2f(q0, 1), dm));
-            o[c].y = pack2(fmaf(ds, byte2f(q0, 2), dm), fmaf(ds, byte2f(q0, 3), dm));
-            o[c].z = pack2(fmaf(ds, byte2f(q1, 0), dm), fmaf(ds, byte2f(q1, 1), dm));
-            o[c].w = pack2(fmaf(ds, byte2f(q1, 2), dm), fmaf(ds, byte2f(q1, 3), dm));
+            // q as float = (2^23 + q) - 2^23 (exact), then one FMA: RN32(ds*q - dm)
+            const f2 a0 = fma2(ds2, add2(magic2(q0, 0), m23), dm2), a1 = fma2(ds2, add2(magic2(q0, 2), m23), dm2);
+            const f2 a2 = fma2(ds2, add2(magic2(q1, 0), m23), dm2), a3 = fma2(ds2, add2(magic2(q1, 2), m23), dm2);
+            o[c].x = pack2(a0.x, a0.y);
+            o[c].y = pack2(a1.x, a1.y);
+            o[c].z = pack2(a2.x, a2.y);
+            o[c].w = pack2(a3.x, a3.y);
         }
     }
 }
@@ -137,9 +169,24 @@ __device__ __forceinline__ void dequant_q4_k(const uint8_t* p, int kb, uint4* ou
 // ---- Q6_K -------------------------------------------------------------------------------------
 // kb: 0..3; half h = kb >> 1, nibble/bit-pair selector gp = kb & 1 (groups g = 2gp, 2gp + 1 of 32 weights):
 //   weight 128h + 32g + l = (ql[64h + 32(g&1) + l] nibble gp) | ((qh[32h + l] >> 2g) & 3) << 4   (q6_k_ref.c:320-336)
-template <int HALF>
-__device__ __forceinline__ void dequant_q6_k(const uint8_t* p, int off, int kb, uint4* out) {
-    const uint8_t* b = p + off;  // 2-byte aligned
+// 8 consecutive 32-bit words starting at a 2-byte aligned address (alignment uniform across the warp)
+template <bool ODD> __device__ __forceinline__ void ld8w(const uint8_t* p, uint32_t w[8]) {
+    if (!ODD) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = q[i];
+    } else {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p - 2);
+        uint32_t r[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) r[i] = q[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(r[i], r[i + 1], 16);
+    }
+}
+
+template <int HALF, bool ODD>
+__device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4* out) {
     const int h = kb >> 1, gp = kb & 1;
     const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
     const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
@@ -147,30 +194,42 @@ __device__ __forceinline__ void dequant_q6_k(const uint8_t* p, int off, int kb, 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         ds[i] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>((scw >> (8 * i)) & 0xffu)));  // exact
+    uint32_t hw[8];
+    ld8w<ODD>(b + 128 + 32 * h, hw);
+    const f2 m32{-8388640.f, -8388640.f};  // -(2^23 + 32): (2^23 + q) + this == q - 32 exactly
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {  // group g = 2gp + gi
         if (HALF != 2 && HALF != gi) continue;
-        const uint8_t* ql = b + 64 * h + 32 * gi;
-        const uint8_t* qh = b + 128 + 32 * h;
-        const int hshift = 4 * gp + 2 * gi;
+        uint32_t lw[8];
+        ld8w<ODD>(b + 64 * h + 32 * gi, lw);
+        // the 2 qh bits of group g sit at bits 2g, 2g+1 of every byte: rotate them to bits 4, 5 (no bits of a
+        // neighbouring byte can reach positions 4, 5: the rotation is by -4, -2, 0 or +2)
+        const uint32_t rot = static_cast<uint32_t>(4 * gp + 2 * gi - 4) & 31u;
         uint4* o = out + ((HALF == 2 && gi == 1) ? 4 : 0);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {  // 8 weights: l = 8*c4 .. 8*c4+7, sub-block 2*gi + (c4 >> 1) of the four
             const float s = ds[2 * gi + (c4 >> 1)];
+            const f2 s2{s, s};
             uint32_t r[4];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
-                const uint32_t lw = ld32_any(ql + 8 * c4 + 4 * v);
-                const uint32_t hw = ld32_any(qh + 8 * c4 + 4 * v);
-                const uint32_t lo = (gp ? (lw >> 4) : lw) & 0x0F0F0F0Fu;
-                const uint32_t hi = ((hw >> hshift) & 0x03030303u) << 4;
-                const uint32_t q = lo | hi;  // four 6-bit quants
-                r[2 * v] = pack2(s * (byte2f(q, 0) - 32.f), s * (byte2f(q, 1) - 32.f));
-                r[2 * v + 1] = pack2(s * (byte2f(q, 2) - 32.f), s * (byte2f(q, 3) - 32.f));
+                const uint32_t lo = (lw[2 * c4 + v] >> (4 * gp)) & 0x0F0F0F0Fu;
+                const uint32_t hr = __funnelshift_r(hw[2 * c4 + v], hw[2 * c4 + v], rot);
+                const uint32_t q = (hr & 0x30303030u) | lo;  // four 6-bit quants
+                const f2 a = mul2(s2, add2(magic2(q, 0), m32)), c = mul2(s2, add2(magic2(q, 2), m32));
+                r[2 * v] = pack2(a.x, a.y);
+                r[2 * v + 1] = pack2(c.x, c.y);
             }
             o[c4] = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
+}
+
+template <int HALF>
+__device__ __forceinline__ void dequant_q6_k(const uint8_t* p, int off, int kb, uint4* out) {
+    const uint8_t* b = p + off;  // 2-byte aligned; (off & 2) is uniform across the block column
+    if (off & 2) dequant_q6_k_al<HALF, true>(b, kb, out);
+    else dequant_q6_k_al<HALF, false>(b, kb, out);
 }
 
 template <int HALF> __device__ __forceinline__ void dequant_part(Unit<0>, const uint8_t* p, int off, int kb, uint4* out) {
