@@ -401,7 +401,7 @@ prefill2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES2; ++s) {
             mbar_init(&x_full[s], 1);
-            mbar_init(&b_full[s], DQ_WARPS + (rank == 0 ? 1 : 0));
+            mbar_init(&b_full[s], DQ_WARPS / 2 + (rank == 0 ? 1 : 0));
             mbar_init(&free_[s], 1);
         }
         for (int u = 0; u < R::DEPTH; ++u) {
@@ -475,33 +475,34 @@ prefill2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
         }
     } else {
-        // ================= dequant warps: 2 threads per weight row (32 weights each) =================
+        // ================= dequant warps: two ping-pong groups of 4 warps =================
+        // Group g (128 threads = the CTA's 128 weight rows) dequantizes the stages kb = g, g+2, ...: every thread
+        // has two MMA periods per stage, which hides the fixed latency of a stage hand-over (barrier waits,
+        // proxy fence, relay to the leader) behind the other group's stage.
         const int dq = threadIdx.x - 64;        // 0..255
         const int dwarp = warp - 2;
         const int urow = dq & 127;              // B row inside this CTA's half tile
-        const int hf = dq >> 7;                 // which 32 of the 64 weights of the stage
+        const int grp = dq >> 7;
         const uint32_t sw = static_cast<uint32_t>(urow & 7);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = grp; kb < num_kb; kb += 2) {
             const int col = kb / R::KB_PER_UNIT, kin = kb % R::KB_PER_UNIT;
             const int slot = col % R::DEPTH;
-            if (kin == 0) mbar_wait(&w_full[slot], static_cast<uint32_t>(col / R::DEPTH) & 1u);
+            mbar_wait(&w_full[slot], static_cast<uint32_t>(col / R::DEPTH) & 1u);
             const int s = kb % STAGES2;
             const uint32_t use = static_cast<uint32_t>(kb / STAGES2);
             if (use > 0) mbar_wait(&free_[s], (use - 1) & 1u);
-            uint4 v[4];
+            uint4 v[8];
             const int off = (col * U::UNIT_BYTES) & 15;
-            const uint8_t* src = units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES;
-            if (hf == 0) dequant_part<0>(U{}, src, off, kin, v);
-            else dequant_part<1>(U{}, src, off, kin, v);
+            dequant64(U{}, units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
             uint8_t* brow = stages + s * STAGE2_BYTES + A2_BYTES + (urow >> 3) * 1024 + (urow & 7) * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(4 * hf + j) ^ sw) << 4)) = v[j];
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(j) ^ sw) << 4)) = v[j];
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&b_full[s]);  // own CTA's barrier (the peer's is relayed to the leader by its warp 1)
-                if (kin == R::KB_PER_UNIT - 1) mbar_arrive(&w_empty[slot]);
+                // last stage of this block column that this group handles -> the unit may be overwritten
+                if (kin + 2 >= R::KB_PER_UNIT || kb + 2 >= num_kb) mbar_arrive(&w_empty[slot]);
             }
         }
         // ---- epilogue: this CTA's 128 TMEM lanes = its 128 tokens of each set, all 256 out-features ----
