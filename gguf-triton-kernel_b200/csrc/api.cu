@@ -118,6 +118,40 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
     return mm(fmt, W, X, ldx, C_out, n_out, ldc, O, T, K, family, stream);
 }
 
+int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc, int64_t O,
+                int64_t T, int64_t K, const ggq_peer_sync* sync, int* ctas_out, void* stream) {
+    const int v = validate(fmt, W, X, C_out, n_out, ldx, ldc, O, T, K);
+    if (v != 0) return v;
+    if (!sync || !ctas_out || sync->world < 1 || sync->world > 8 || sync->rank < 0 || sync->rank >= sync->world ||
+        !sync->flags_local || !sync->counter)
+        return GGQ_E_POINTER;
+    if (O < 16 || T < 1 || T > 16 || K < fmt_qk(fmt)) return GGQ_E_FAMILY;
+    MmArgs a{};
+    a.W = static_cast<const uint8_t*>(W);
+    a.X = X;
+    for (int i = 0; i < n_out; ++i) a.C[i] = C_out[i];
+    a.n_out = n_out;
+    a.ldx = ldx;
+    a.ldc = ldc;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    a.stream = static_cast<cudaStream_t>(stream);
+    PeerSync ps{};
+    ps.flags_local = sync->flags_local;
+    for (int i = 0; i < 8; ++i) ps.flags_peer[i] = sync->flags_peer[i];
+    ps.counter = sync->counter;
+    ps.x_ready = sync->x_ready;
+    ps.epoch = sync->epoch;
+    ps.counter_target = sync->counter_base;  // the planner adds the grid size
+    ps.rank = sync->rank;
+    ps.world = sync->world;
+    a.sync = &ps;
+    a.ctas_out = ctas_out;
+    if (!decode_supports(fmt, a)) return GGQ_E_FAMILY;
+    return launch_decode(fmt, a);
+}
+
 int ggq_dequant_q8_0_f16(const void* W, void* out, int64_t O, int64_t K, void* stream) {
     return dequant(GGQ_Q8_0, W, out, O, K, stream);
 }

@@ -6,6 +6,16 @@
 
 namespace ggq {
 
+// In-kernel N-split exchange (see ggq_peer_sync in include/ggq.h); world == 0 means disabled.
+struct PeerSync {
+    uint32_t* flags_local;
+    uint32_t* flags_peer[8];
+    uint32_t* counter;
+    const uint32_t* x_ready;
+    uint32_t epoch, counter_target;
+    int rank, world;
+};
+
 struct MmArgs {
     const uint8_t* W;     // packed weight rows
     const void* X;        // fp16 [T, ldx]
@@ -14,6 +24,8 @@ struct MmArgs {
     int64_t ldx, ldc;
     int64_t O, T, K;
     cudaStream_t stream;
+    const PeerSync* sync;  // decode family only; nullptr = plain call
+    int* ctas_out;
 };
 
 // Output pointers passed to kernels by value.  n > 1 = the same tile is also stored to peer-mapped

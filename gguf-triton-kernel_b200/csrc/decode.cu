@@ -50,6 +50,7 @@ struct Params {
     int num_batches;
     int stages;
     int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
+    PeerSync sync;      // world == 0: no cross-GPU synchronisation
     uint32_t x_stride;  // bytes between token rows in shared memory
     uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red;
 };
@@ -149,6 +150,12 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
                 __syncthreads();  // every warp is done with the previous slice's x / tbl
                 if (tid == 0) {
+                    if (p.sync.world > 0 && p.sync.x_ready != nullptr && batch == 0 && slice == 0) {
+                        // activations are produced by rank 0 (peer memory): wait for its "ready" word of this step
+                        while (ld_acquire_sys(p.sync.x_ready) < p.sync.epoch) {
+                        }
+                        fence_proxy_async_all();  // the TMA engine (async proxy) reads what we just acquired
+                    }
                     mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
                     for (int t = 0; t < p.T; ++t)
                         bulk_g2s(xs + t * p.x_stride, p.X + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
@@ -237,6 +244,24 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             }
         }
     }
+
+    if (p.sync.world > 1) {
+        // ---- fused N-split exchange: every tile above was stored into all ranks' C; tell the peers, wait for theirs
+        __threadfence_system();   // my stores (possibly to peer memory) are ordered before the signal below
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t arrived = atomicAdd(p.sync.counter, 1u) + 1u;
+            if (arrived == p.sync.counter_target) {   // last CTA of this rank
+                __threadfence_system();
+                for (int r = 0; r < p.sync.world; ++r)
+                    if (r != p.sync.rank) st_release_sys(p.sync.flags_peer[r] + p.sync.rank, p.sync.epoch);
+                for (int r = 0; r < p.sync.world; ++r)
+                    if (r != p.sync.rank)
+                        while (ld_acquire_sys(p.sync.flags_local + r) < p.sync.epoch) {
+                        }
+            }
+        }
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -270,6 +295,7 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     const int SMEM_LIMIT = OCC == 2 ? SMEM_LIMIT_2 : dec::SMEM_LIMIT;
     pl.nw = NW;
     pl.occ = OCC;
+    if (a.sync) p.sync = *a.sync;
     {
         static const int skip = [] { const char* e = getenv("GGQ_DECODE_NOCOMPUTE"); return (e && e[0] == '1') ? 1 : 0; }();
         p.dbg_skip_compute = skip;
@@ -330,6 +356,8 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt - 1) / wt));
     const int rounds = (p.num_tiles + pl.grid * wt - 1) / (pl.grid * wt);
     p.num_batches = (rounds + at - 1) / at;
+    if (a.sync) p.sync.counter_target = a.sync->counter_target + static_cast<uint32_t>(pl.grid);  // base + CTAs of this launch
+    if (a.ctas_out) *a.ctas_out = pl.grid;
     return true;
 }
 
@@ -368,6 +396,7 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
 
 template <int FMT>
 static int launch_fmt(const MmArgs& a) {
+    if (a.sync && a.T > 16) return GGQ_E_FAMILY;  // the fused exchange is a single-pass feature
     for (int64_t t0 = 0; t0 < a.T; t0 += 16) {  // T > 16: 16-token passes (weights re-read per pass)
         MmArgs s = a;
         s.X = static_cast<const __half*>(a.X) + t0 * a.ldx;

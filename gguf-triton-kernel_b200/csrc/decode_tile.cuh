@@ -265,16 +265,16 @@ GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
 // Per (block, token) the staging pass turns the raw activations into what compute_q4_k reads:
 // the permuted fp16 row (in place) and the bf16 hi/lo split of the eight 32-activation sums, laid out
 // as the B fragment of the min-term MMA: xb[(blk * TPAD + token) * 4 + t] = {bf16x2(hi_2t, hi_2t+1),
-// bf16x2(lo_2t, lo_2t+1)}.  `x` points at the 256 activations of the block (16-byte aligned).
-GGQ_DEV void q4k_stage_block(uint8_t* x, uint2* xb_entry /* 4 entries */, bool token_valid) {
+// bf16x2(lo_2t, lo_2t+1)}.  One call handles one entry = 64 activations (sub-blocks 2t, 2t+1).
+GGQ_DEV void q4k_stage_pair(uint8_t* x, uint2* xb_entry, bool token_valid) {
+    // one B-fragment entry: sub-blocks 2t and 2t+1 (64 activations at `x`)
     if (!token_valid) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) xb_entry[t] = uint2{0u, 0u};
+        *xb_entry = uint2{0u, 0u};
         return;
     }
-    uint32_t hi[8], lo[8];
+    uint32_t hi[2], lo[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 2; ++j) {
         float sum = 0.f;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -299,9 +299,7 @@ GGQ_DEV void q4k_stage_block(uint8_t* x, uint2* xb_entry /* 4 entries */, bool t
         hi[j] = h >> 16;
         lo[j] = bf16_bits_rn(sum - u2f(h));
     }
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-        xb_entry[t] = uint2{hi[2 * t] | (hi[2 * t + 1] << 16), lo[2 * t] | (lo[2 * t + 1] << 16)};
+    *xb_entry = uint2{hi[0] | (hi[1] << 16), lo[0] | (lo[1] << 16)};
 }
 
 template <int NT>
@@ -501,10 +499,11 @@ GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int n
     constexpr int TPAD = 8 * NT;
     if (FMT == 1) {
         uint2* xb = reinterpret_cast<uint2*>(tbl);
-        const int nblk = ne / 256;
-        for (int idx = tid; idx < nblk * TPAD; idx += nthreads) {
-            const int b = idx / TPAD, col = idx % TPAD;
-            q4k_stage_block(xs + (col < T ? col : 0) * x_stride + b * 512, xb + (b * TPAD + col) * 4, col < T);
+        const int nent = ne / 64;  // entries per token
+        for (int idx = tid; idx < nent * TPAD; idx += nthreads) {
+            const int e = idx % nent, col = idx / nent;  // consecutive threads -> consecutive 128-byte pieces of a row
+            const int b = e >> 2, t = e & 3;
+            q4k_stage_pair(xs + (col < T ? col : 0) * x_stride + e * 128, xb + (b * TPAD + col) * 4 + t, col < T);
         }
     } else {
         const int ngrp = ne / G::GROUP;

@@ -10,8 +10,13 @@ are exchanged so that every rank ends up with the full C[T, O].  Two exchange pa
            copy to [T, O].  Baseline path.
   "fused"  no collective kernel at all: the GEMM/GEMV epilogue stores each output tile straight into the
            [T, O] buffers of ALL ranks through NVLink peer mappings (torch symmetric memory supplies
-           the peer pointers; ggq_mm_ex takes them as n_out outputs with ldc = O), followed by one
-           symmetric-memory barrier.  The transfer overlaps the math tile by tile.
+           the peer pointers; the kernels take them as n_out outputs with ldc = O), so the transfer
+           overlaps the math tile by tile.  For T <= 16 the whole exchange lives inside the ONE decode
+           kernel (ggq_mm_sync): ranks != 0 read the activations directly from rank 0's buffer over
+           NVLink after acquiring its "ready" word, and the last CTA of every rank publishes / awaits
+           per-rank epoch flags in peer memory, so kernel completion == C[T, O] complete everywhere.
+           For T > 16 (prefill) the activations are NCCL-broadcast and a symmetric-memory barrier
+           follows the GEMM (its cost is negligible next to a millisecond GEMM).
 
 `mm_fn` is injectable so the host logic (sharding arithmetic, exchange layout) is testable on CPU with
 the gloo backend and a stand-in matmul.
@@ -83,30 +88,74 @@ class NSplitLinear:
         elif mode != "nccl":
             raise ValueError(mode)
 
-    # ---- fused path: peer-mapped output buffers ----
+    # ---- fused path: peer-mapped buffers ----
     def _init_symm(self):
         import torch.distributed._symmetric_memory as symm_mem
         dev = self.A.device
-        self._out = symm_mem.empty((self.max_tokens, self.O), dtype=torch.float16, device=dev)
+        self._out = symm_mem.empty((2, self.max_tokens, self.O), dtype=torch.float16, device=dev)   # double-buffered C
         self._symm = symm_mem.rendezvous(self._out, self.group)
-        col_off = self.lo * 2  # bytes: this rank's column offset inside every rank's [T, O] buffer
-        self._peer_ptrs = [int(p) + col_off for p in self._symm.buffer_ptrs]
-        # own buffer first (purely cosmetic: all are written)
-        self._peer_ptrs = [self._peer_ptrs[self.rank]] + [p for i, p in enumerate(self._peer_ptrs) if i != self.rank]
+        self._xbuf = symm_mem.empty((2, min(self.max_tokens, 16), self.K), dtype=torch.float16, device=dev)
+        self._xsymm = symm_mem.rendezvous(self._xbuf, self.group)
+        self._flags = symm_mem.empty((16,), dtype=torch.int32, device=dev)  # [0..7] peer epochs, [8] x ready
+        self._flags.zero_()
+        self._fsymm = symm_mem.rendezvous(self._flags, self.group)
+        self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._counter_base = 0
+        self._epoch = 0
+        torch.cuda.synchronize(dev)
+        self._symm.barrier(channel=0)  # everyone's flags are zeroed before anyone signals
+
+    def _out_ptrs(self, cur: int) -> list[int]:
+        off = (cur * self.max_tokens * self.O + self.lo) * 2   # buffer `cur`, this rank's column offset (bytes)
+        ptrs = [int(p) + off for p in self._symm.buffer_ptrs]
+        return [ptrs[self.rank]] + [p for i, p in enumerate(ptrs) if i != self.rank]
+
+    def _forward_fused_decode(self, X: torch.Tensor, T: int, broadcast: bool) -> torch.Tensor:
+        ext = self._ext
+        self._epoch += 1
+        cur = self._epoch & 1
+        x_ready = 0
+        if broadcast and self.world > 1:
+            xoff = cur * self._xbuf.shape[1] * self.K * 2
+            if self.rank == 0:
+                self._xbuf[cur, :T].copy_(X)              # stream-ordered: lands before the ready word
+                self._flags[8:9].fill_(self._epoch)
+                x_ptr = self._xbuf.data_ptr() + xoff
+            else:
+                x_ptr = int(self._xsymm.buffer_ptrs[0]) + xoff    # rank 0's buffer over NVLink
+                x_ready = int(self._fsymm.buffer_ptrs[0]) + 8 * 4
+        else:
+            x_ptr = X.data_ptr()
+        sync = ext.PeerSync()
+        sync.flags_local = self._flags.data_ptr()
+        for r in range(self.world):
+            sync.flags_peer[r] = int(self._fsymm.buffer_ptrs[r])
+        sync.counter = self._counter.data_ptr()
+        sync.x_ready = x_ready
+        sync.epoch = self._epoch
+        sync.counter_base = self._counter_base & 0xFFFFFFFF
+        sync.rank, sync.world = self.rank, self.world
+        ctas = ext.mm_sync(self._fmt_id, self.A, x_ptr, self._out_ptrs(cur), self.O, self.per, T, self.K, sync)
+        self._counter_base += ctas
+        return self._out[cur, :T]
 
     def forward(self, X: torch.Tensor, *, broadcast: bool = True) -> torch.Tensor:
         """X: fp16 [T, K] (valid on rank 0 when `broadcast`).  Returns C[T, O] on every rank."""
         T = X.shape[0]
-        if broadcast and self.world > 1:
-            dist.broadcast(X, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
-                           group=self.group)
         if self.mode == "fused":
             if T > self.max_tokens:
                 raise ValueError(f"T={T} exceeds max_tokens={self.max_tokens} of the symmetric buffer")
+            if T <= 16 and self.per >= 16:
+                return self._forward_fused_decode(X, T, broadcast)
+            if broadcast and self.world > 1:
+                dist.broadcast(X, src=0, group=self.group)
             self._symm.barrier(channel=0)   # every rank has finished reading the previous result
-            self._ext.mm_ex(self._fmt_id, self.A, X, self._peer_ptrs, self.O, self.per, T, self.K)
+            self._ext.mm_ex(self._fmt_id, self.A, X, self._out_ptrs(0), self.O, self.per, T, self.K)
             self._symm.barrier(channel=1)   # every rank's tiles have landed everywhere
-            return self._out[:T]
+            return self._out[0, :T]
+        if broadcast and self.world > 1:
+            dist.broadcast(X, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
+                           group=self.group)
         if self.mm_fn is not None:
             c = self.mm_fn(self.A, X, self.per, T, self.K)
         else:

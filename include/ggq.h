@@ -80,6 +80,33 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
               int64_t O, int64_t T, int64_t K, int family, void* stream);
 
 /*
+ * Decode-family GEMV/skinny GEMM with the N-split exchange fused INTO the kernel (T <= 16):
+ *   - activations may live in another rank's memory (X = NVLink peer pointer to rank 0's buffer); if
+ *     `x_ready` is non-NULL every CTA first waits until *x_ready >= epoch (acquire, system scope);
+ *   - every output tile is stored to all C_out[i] (own + peer [T, ldc] buffers);
+ *   - at the end the last CTA publishes `epoch` into flags_peer[p][rank] of every peer (release, system
+ *     scope) and waits until every peer has published its own into flags_local[p]: when the kernel
+ *     completes, the full C[T, O] is present in this rank's buffer.  No NCCL call, no separate barrier kernel.
+ * flags_local / flags_peer[p] are uint32[8] arrays in symmetric (peer-mapped) memory, zero-initialised;
+ * `counter` is a zero-initialised uint32 in local device memory; `epoch` must increase by 1 per call on all
+ * ranks; `counter_base` is the value of *counter before this call (the library adds the grid size).
+ * Every rank of the group must make the matching call or the waiting ranks never finish.
+ */
+typedef struct ggq_peer_sync {
+    uint32_t* flags_local;
+    uint32_t* flags_peer[8];
+    uint32_t* counter;
+    const uint32_t* x_ready;
+    uint32_t epoch;
+    uint32_t counter_base;
+    int32_t rank, world;
+} ggq_peer_sync;
+
+/* Returns 0 and writes the number of CTAs launched to *ctas_out (the caller advances counter_base by it). */
+int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc,
+                int64_t O, int64_t T, int64_t K, const ggq_peer_sync* sync, int* ctas_out, void* stream);
+
+/*
  * Dequantize packed rows to fp16 [O, K] with the SAME device functions the prefill GEMM uses.
  * Bit-exact targets: utils/quantize/q8_0.py:52-100 dequantize_q8_0, q4_k.py:146-158 dequantize_q4_k,
  * q6_k.py:138-159 dequantize_q6_k (fp32 there; `.half()` of it here).
