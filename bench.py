@@ -283,13 +283,24 @@ def run_ours(args):
         from multigpu import nsplit
         layer = nsplit.NSplitLinear(FMT, W, O, K, mode=args.exchange, max_tokens=16)
 
+    fused = world > 1 and args.exchange == "fused"
+    if fused and rank == 0:
+        layer.set_resident_input(x_dev)
+
     def step_device():
-        if world > 1:
+        if fused:
+            layer.forward(None, T=T)      # activations resident in rank 0's peer-visible buffer (set_resident_input)
+        elif world > 1:
             layer.forward(x_dev)          # broadcast X, per-rank GEMV on the shard, exchange -> [T, O] everywhere
         else:
             ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard)
 
     def step_e2e():
+        if fused:
+            if rank == 0:
+                layer.input_buffer(T).copy_(x_host, non_blocking=True)   # H2D straight into the peer-visible buffer
+            c_host.copy_(layer.forward(None, T=T), non_blocking=True)
+            return
         x_dev.copy_(x_host, non_blocking=True)
         if world > 1:
             c_host.copy_(layer.forward(x_dev), non_blocking=True)

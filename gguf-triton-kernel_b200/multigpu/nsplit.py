@@ -104,44 +104,80 @@ class NSplitLinear:
         self._epoch = 0
         torch.cuda.synchronize(dev)
         self._symm.barrier(channel=0)  # everyone's flags are zeroed before anyone signals
+        self._prepare_fast_path()
 
     def _out_ptrs(self, cur: int) -> list[int]:
         off = (cur * self.max_tokens * self.O + self.lo) * 2   # buffer `cur`, this rank's column offset (bytes)
         ptrs = [int(p) + off for p in self._symm.buffer_ptrs]
         return [ptrs[self.rank]] + [p for i, p in enumerate(ptrs) if i != self.rank]
 
-    def _forward_fused_decode(self, X: torch.Tensor, T: int, broadcast: bool) -> torch.Tensor:
+    def _prepare_fast_path(self):
+        """Everything that does not change from step to step is built once: the per-step host cost of the fused
+        path is a handful of attribute writes and one ctypes call (the kernels take ~15-70 us)."""
+        import ctypes
         ext = self._ext
-        self._epoch += 1
-        cur = self._epoch & 1
-        x_ready = 0
-        if broadcast and self.world > 1:
-            xoff = cur * self._xbuf.shape[1] * self.K * 2
-            if self.rank == 0:
-                self._xbuf[cur, :T].copy_(X)              # stream-ordered: lands before the ready word
-                self._flags[8:9].fill_(self._epoch)
-                x_ptr = self._xbuf.data_ptr() + xoff
-            else:
-                x_ptr = int(self._xsymm.buffer_ptrs[0]) + xoff    # rank 0's buffer over NVLink
-                x_ready = int(self._fsymm.buffer_ptrs[0]) + 8 * 4
-        else:
-            x_ptr = X.data_ptr()
+        self._lib = ext.lib()
+        self._lib.ggq_mm_sync.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ext.PeerSync),
+                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        self._lib.ggq_mm_sync.restype = ctypes.c_int
+        self._out_arr = [(ctypes.c_void_p * self.world)(*self._out_ptrs(c)) for c in (0, 1)]
+        xrows = self._xbuf.shape[1]
+        self._x_local = [self._xbuf.data_ptr() + c * xrows * self.K * 2 for c in (0, 1)]
+        self._x_rank0 = [int(self._xsymm.buffer_ptrs[0]) + c * xrows * self.K * 2 for c in (0, 1)]
+        self._x_ready_ptr = int(self._fsymm.buffer_ptrs[0]) + 8 * 4
         sync = ext.PeerSync()
         sync.flags_local = self._flags.data_ptr()
         for r in range(self.world):
             sync.flags_peer[r] = int(self._fsymm.buffer_ptrs[r])
         sync.counter = self._counter.data_ptr()
-        sync.x_ready = x_ready
+        sync.rank, sync.world = self.rank, self.world
+        self._sync = sync
+        self._sync_ref = ctypes.byref(sync)
+        self._ctas = ctypes.c_int(0)
+        self._ctas_ref = ctypes.byref(self._ctas)
+        self._a_ptr = self.A.data_ptr()
+        self._flag_x = self._flags[8:9]   # rank 0's "activations of epoch e are in place" word
+
+    def input_buffer(self, T: int) -> torch.Tensor:
+        """Rank 0: the symmetric [T, K] buffer the NEXT fused decode step reads its activations from.  Writing the
+        activations there directly (e.g. as the H2D copy target) and calling forward(None, T=T) skips the staging copy."""
+        return self._xbuf[(self._epoch + 1) & 1, :T]
+
+    def set_resident_input(self, X: torch.Tensor) -> None:
+        """Rank 0: keep the same activations resident in both symmetric slots (benchmarking `forward(None, T=T)`)."""
+        self._xbuf[:, :X.shape[0]].copy_(X)
+
+    def _forward_fused_decode(self, X, T: int, broadcast: bool) -> torch.Tensor:
+        self._epoch += 1
+        cur = self._epoch & 1
+        sync = self._sync
+        sync.x_ready = 0
+        if broadcast and self.world > 1:
+            if self.rank == 0:
+                if X is not None and X.data_ptr() != self._x_local[cur]:
+                    self._xbuf[cur, :T].copy_(X)          # stream-ordered: lands before the ready word
+                self._flag_x.fill_(self._epoch)             # stream-ordered after the activations landed
+                x_ptr = self._x_local[cur]
+            else:
+                x_ptr = self._x_rank0[cur]                # rank 0's buffer over NVLink
+                sync.x_ready = self._x_ready_ptr
+        else:
+            x_ptr = X.data_ptr()
         sync.epoch = self._epoch
         sync.counter_base = self._counter_base & 0xFFFFFFFF
-        sync.rank, sync.world = self.rank, self.world
-        ctas = ext.mm_sync(self._fmt_id, self.A, x_ptr, self._out_ptrs(cur), self.O, self.per, T, self.K, sync)
-        self._counter_base += ctas
+        rc = self._lib.ggq_mm_sync(self._fmt_id, self._a_ptr, x_ptr, self.K, self._out_arr[cur], self.world, self.O, self.per,
+                                   T, self.K, self._sync_ref, self._ctas_ref, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            self._ext.check(rc, "ggq_mm_sync")
+        self._counter_base += self._ctas.value
         return self._out[cur, :T]
 
-    def forward(self, X: torch.Tensor, *, broadcast: bool = True) -> torch.Tensor:
-        """X: fp16 [T, K] (valid on rank 0 when `broadcast`).  Returns C[T, O] on every rank."""
-        T = X.shape[0]
+    def forward(self, X, *, broadcast: bool = True, T: int | None = None) -> torch.Tensor:
+        """X: fp16 [T, K] (valid on rank 0 when `broadcast`; None + T = the activations were written into
+        input_buffer(T), fused decode path only).  Returns C[T, O] on every rank."""
+        T = X.shape[0] if X is not None else T
         if self.mode == "fused":
             if T > self.max_tokens:
                 raise ValueError(f"T={T} exceeds max_tokens={self.max_tokens} of the symmetric buffer")
