@@ -360,7 +360,7 @@ def run_ours(args):
                      "frac_of_8TBps_nominal": achieved / 8000.0, "us_per_launch": ms_k * 1e3,
                      "algorithmic_bytes_per_launch": k_bytes,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/, N=1 only)
-                     "traffic": 295552512 + 4535296 if world == 1 else None},
+                     "traffic": 295552512 + 3876096 if world == 1 else None},
         "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_rows} of {O} rows, one pass ({cpu_dt:.1f} s), numpy oracle port of kernels/cpu_impls"},
         "parity": parity,
