@@ -14,9 +14,9 @@
 // Integer -> fp16 costs one LOP3/PRMT per weight PAIR: an integer < 1024 placed in the low mantissa
 // bits of a half whose exponent field is zero IS the subnormal value n * 2^-24, which the tensor core
 // multiplies exactly; the power of two is folded into the fp32 scale.  (The classic 0x6400 "1024 + n"
-// magic is avoided on purpose: HMMA truncates when it aligns addends, so a bias of 1024 costs ~10 bits
-// of the fp32 accumulator — measured 2e-4 relative error on B200 — while the subnormal form keeps the
-// addends at the magnitude of the signal.)  Products are exact and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
+// magic is avoided on purpose: its bias has to be cancelled in fp32 afterwards, which costs ~10 bits of
+// the accumulator — 8e-6 vs 2e-7 relative error in the host emulator — while the subnormal form keeps
+// the addends at the magnitude of the signal.)  Products are exact and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
 // agree, lane t of a quad always takes the 4 weights that share one 32-bit word and the 4 matching
 // consecutive activations.
 //
