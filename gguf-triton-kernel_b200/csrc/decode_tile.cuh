@@ -302,8 +302,10 @@ GGQ_DEV void q4k_stage_pair(uint8_t* x, uint2* xb_entry, bool token_valid) {
     *xb_entry = uint2{hi[0] | (hi[1] << 16), lo[0] | (lo[1] << 16)};
 }
 
-template <int NT>
-GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
+// FULL = the sub-step holds all PREP_BLOCKS blocks: no per-block bounds checks, so the whole sub-step is one basic
+// block and ptxas can hoist the next chunk's shared-memory loads over the current chunk's math.
+template <int NT, bool FULL>
+GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     using G = Geo<1>;
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
     const uint8_t* r1 = r0 + 8 * G::SLOT;
@@ -311,7 +313,7 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint2* xbt = reinterpret_cast<const uint2*>(s.tbl);
 #pragma unroll
     for (int i = 0; i < G::PREP_BLOCKS; ++i) {
-        if (i >= s.nblk) break;
+        if (!FULL && i >= s.nblk) break;
         const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
         const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
         const uint8_t* e0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
@@ -381,6 +383,12 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             }
         }
     }
+}
+
+template <int NT>
+GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
+    if (s.nblk == Geo<1>::PREP_BLOCKS) compute_q4_k_impl<NT, true>(L, s, acc);
+    else compute_q4_k_impl<NT, false>(L, s, acc);
 }
 
 // =============================================================================================
@@ -482,7 +490,7 @@ GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint8_t* r1 = r0 + 8 * G::SLOT;
 #pragma unroll
     for (int i = 0; i < G::PREP_BLOCKS; i += 2) {  // chunk starts at an even block: even blocks 4-byte aligned
-        if (i >= s.nblk) break;
+        // (rows are whole 16-byte vectors => K/256 is a multiple of 8 => every sub-step is full: no bounds check)
         compute_q6_k_block<NT, false>(L, s, i, r0, r1, acc);
         compute_q6_k_block<NT, true>(L, s, i + 1, r0, r1, acc);
     }

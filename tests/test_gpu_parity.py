@@ -255,3 +255,60 @@ def test_full_size_properties(ext, fmt):
     rows = np.random.default_rng(3).choice(M, 96, replace=False)
     Asub = np.concatenate([A[r * rowB:(r + 1) * rowB] for r in rows])
     check_tier1(fmt, Asub, X1, len(rows), 4, K, C1[:, rows].cpu().numpy().astype(np.float16), "full-size sample")
+
+
+# ---- extended C-ABI form: strides, several outputs, fused-exchange entry point on one rank ---------
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("family,N", [(1, 5), (2, 7), (3, 96)])
+def test_mm_ex_strides_and_multiple_outputs(ext, fmt, family, N):
+    M, K = 80, 2048
+    ldx, ldc = K + 64, M + 24
+    A = orc.random_blocks(fmt, M, K, seed=21)
+    X = rand_x(N, K, 22)
+    Xp = torch.zeros((N, ldx), dtype=torch.float16, device="cuda:0")
+    Xp[:, :K] = dev(X)
+    C1 = torch.full((N, ldc), 7.0, dtype=torch.float16, device="cuda:0")
+    C2 = torch.full((N, ldc), 7.0, dtype=torch.float16, device="cuda:0")
+    ext.mm_ex(ext.FMT_ID[fmt], dev(A), Xp, [C1.data_ptr(), C2.data_ptr()], ldc, M, N, K, family=family, ldx=ldx)
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    assert torch.all(C1[:, M:] == 7.0)  # nothing outside the [N, M] window is touched
+    check_tier1(fmt, A, X, M, N, K, C1[:, :M].cpu().numpy(), "mm_ex")
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_mm_sync_single_rank(ext, fmt):
+    """ggq_mm_sync with world = 1: the in-kernel epoch/flag machinery degenerates to a plain call."""
+    M, N, K = 300, 3, 2048
+    A = orc.random_blocks(fmt, M, K, seed=31)
+    X = rand_x(N, K, 32)
+    Ad, Xd = dev(A), dev(X)
+    C = torch.zeros((N, M), dtype=torch.float16, device="cuda:0")
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda:0")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    sync = ext.PeerSync()
+    sync.flags_local = flags.data_ptr()
+    sync.flags_peer[0] = flags.data_ptr()
+    sync.counter = counter.data_ptr()
+    sync.x_ready = 0
+    sync.rank, sync.world = 0, 1
+    base = 0
+    for epoch in (1, 2, 3):
+        sync.epoch, sync.counter_base = epoch, base
+        base += ext.mm_sync(ext.FMT_ID[fmt], Ad, Xd.data_ptr(), [C.data_ptr()], M, M, N, K, sync)
+    torch.cuda.synchronize()
+    assert base > 0 and counter.item() == 0  # a single rank has nobody to signal: the tail is skipped entirely
+    check_tier1(fmt, A, X, M, N, K, C.cpu().numpy(), "mm_sync")
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_prefill_matches_decode_on_the_same_problem(ext, fmt):
+    """The two fast families are independent implementations; on a shape both accept they must agree to
+    fp16 output rounding (the decode family does not round weights to fp16, so not bit-identical)."""
+    M, N, K = 512, 16, 2048
+    A = orc.random_blocks(fmt, M, K, seed=41)
+    X = rand_x(N, K, 42)
+    Cd = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_DECODE).astype(np.float32)
+    Cp = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_PREFILL).astype(np.float32)
+    mx, fro = orc.tier1_errors(Cd, Cp)
+    assert fro < 1e-3 and mx < 5e-3, (mx, fro)
