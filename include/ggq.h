@@ -115,6 +115,17 @@ int ggq_dequant_q8_0_f16(const void* W, void* out, int64_t O, int64_t K, void* s
 int ggq_dequant_q4_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream);
 int ggq_dequant_q6_k_f16(const void* W, void* out, int64_t O, int64_t K, void* stream);
 
+/*
+ * "Next" rows of the path, same conventions:
+ *   ggq_quantize_q8_0_f16   fp16 x[n] -> Q8_0 blocks (n/32 * 34 B), byte-identical to utils/quantize/q8_0.py:4-49
+ *   ggq_quantize_q8_1_f16   fp16 x[n] -> Q8_1 blocks (n/32 * 36 B), byte-identical to utils/quantize/q8_1.py:18-70
+ *   ggq_dequant_q6_k_f32    fp32 [O, K], bit-identical to utils/quantize/q6_k.py:138-159 (which returns fp32)
+ * n must be a multiple of 32 (the reference raises ValueError, q8_0.py:14-15).
+ */
+int ggq_quantize_q8_0_f16(const void* x, void* out, int64_t n, void* stream);
+int ggq_quantize_q8_1_f16(const void* x, void* out, int64_t n, void* stream);
+int ggq_dequant_q6_k_f32(const void* W, void* out, int64_t O, int64_t K, void* stream);
+
 /* Bytes of a packed [O, K] weight (O * K/QK * block bytes), or GGQ_E_* (<0). */
 int64_t ggq_packed_nbytes(int fmt, int64_t O, int64_t K);
 

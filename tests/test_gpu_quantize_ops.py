@@ -1,0 +1,62 @@
+"""GPU mirrors of the reference's utils/quantize functions next to the mmq path: packers must be
+byte-identical, dequantizers bit-identical, to the oracle (which is pinned to the reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ggq_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _x(shape, seed, scale=1.0):
+    x = (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float16)
+    x.reshape(-1)[:64] = 0          # all-zero groups (d = 1 for Q8_0, d = 0 for Q8_1)
+    x.reshape(-1)[64:67] = [np.float16(0.5), np.float16(-0.5), np.float16(1.5)]  # ties for round-half-even
+    return x
+
+
+@pytest.mark.parametrize("shape,scale", [((4, 64), 1.0), ((33, 1024), 0.01), ((7, 4096), 30.0)])
+def test_q8_packers_byte_identical(shape, scale):
+    from utils.quantize.q8_0 import quantize_to_q8_0
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    x = _x(shape, 5, scale)
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(quantize_to_q8_0(xd).cpu().numpy(), orc.quantize_to_q8_0(x))
+    assert np.array_equal(quantize_to_q8_1(xd).cpu().numpy(), orc.quantize_to_q8_1(x))
+    with pytest.raises(ValueError):
+        quantize_to_q8_0(torch.zeros(33, dtype=torch.float16, device="cuda"))
+
+
+def test_golden_q8_packers(golden):
+    from utils.quantize.q8_0 import quantize_to_q8_0
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    for c in golden["q8_0"]:
+        assert np.array_equal(quantize_to_q8_0(torch.from_numpy(c["W"]).cuda()).cpu().numpy(), c["A"])
+        assert np.array_equal(quantize_to_q8_1(torch.from_numpy(c["X"]).cuda()).cpu().numpy(), c["B"])
+
+
+def test_dequantize_mirrors(golden):
+    from utils.quantize.q4_k import dequantize_q4_k
+    from utils.quantize.q6_k import dequantize_q6_k
+    from utils.quantize.q8_0 import dequantize_q8_0
+    for fmt, fn in (("q8_0", dequantize_q8_0), ("q4_k", dequantize_q4_k), ("q6_k", dequantize_q6_k)):
+        for c in golden[fmt]:
+            got = fn(torch.from_numpy(c["A"]).cuda(), (c["M"], c["K"])).cpu().numpy()
+            assert got.dtype == c["D"].dtype and got.shape == c["D"].shape
+            bits = np.uint32 if got.dtype == np.float32 else np.uint16
+            assert np.array_equal(got.view(bits), c["D"].view(bits)), fmt
+
+
+def test_reference_style_pipeline_on_gpu():
+    """quantize (GPU) -> mmq (GPU) as in test/test_mmq_q8_0.py:27-36, everything resident on the device."""
+    from kernels.mmq_q8_0 import mmq_q8_0
+    from utils.quantize.q8_0 import quantize_to_q8_0
+    M, N, K = 64, 4, 1024
+    W = torch.randn(M, K, dtype=torch.float16, device="cuda")
+    X = torch.randn(N, K, dtype=torch.float16, device="cuda")
+    A = quantize_to_q8_0(W)
+    C = mmq_q8_0(A, X, M, N, K)
+    ref = orc.ref32("q8_0", A.cpu().numpy(), X.cpu().numpy(), M, N, K)
+    mx, fro = orc.tier1_errors(C.float().cpu().numpy(), ref)
+    assert mx <= orc.TIER1_MAX and fro <= orc.TIER1_FRO
