@@ -157,7 +157,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 * O / rows, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "int8 block dots + fp16 accumulate (reference CPU arithmetic)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16", "arithmetic": "Q8_1 activations, int8 block dots, fp16 accumulate (reference CPU arithmetic)",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,7 +282,14 @@ def run_ours(args):
     layer = None
     if world > 1:
         from multigpu import nsplit
-        layer = nsplit.NSplitLinear(FMT, W, O, K, mode=args.exchange, max_tokens=16)
+        try:
+            layer = nsplit.NSplitLinear(FMT, W, O, K, mode=args.exchange, max_tokens=16)
+        except Exception as e:  # no peer-mappable (symmetric) memory on this box: NCCL exchange instead
+            if args.exchange != "fused":
+                raise
+            print(f"[bench] fused exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            args.exchange = "nccl"
+            layer = nsplit.NSplitLinear(FMT, W, O, K, mode="nccl", max_tokens=16)
 
     fused = world > 1 and args.exchange == "fused"
     if fused and rank == 0:
@@ -345,7 +353,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 (fp16 activations x in-register dequantized weights, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f16", "arithmetic": "fp16 activations x in-register dequantized weights, fp32 accumulate, fp16 out",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": L2_NOTE,
                    "parallelism": f"N-split x{world}, exchange={args.exchange}" if world > 1 else "single GPU",
                    "fmt": FMT, "O": O, "K": K, "T": T},

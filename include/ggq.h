@@ -126,6 +126,14 @@ int ggq_quantize_q8_0_f16(const void* x, void* out, int64_t n, void* stream);
 int ggq_quantize_q8_1_f16(const void* x, void* out, int64_t n, void* stream);
 int ggq_dequant_q6_k_f32(const void* W, void* out, int64_t O, int64_t K, void* stream);
 
+/*
+ * Reference-arithmetic mode: XQ = activations packed as Q8_1 (T rows of K/32 36-byte blocks, e.g. by
+ * ggq_quantize_q8_1_f16); integer block dots and fp16 accumulation in the exact operation order of
+ * kernels/cpu_impls/mmq_{q8_0,q4_k,q6_k}_q8_1_cpu.py, so C[T, O] equals their result bit for bit.  A parity
+ * tool (one thread per output), not a fast path.
+ */
+int ggq_mm_ref_q8_1(int fmt, const void* W, const void* XQ, void* C, int64_t O, int64_t T, int64_t K, void* stream);
+
 /* Bytes of a packed [O, K] weight (O * K/QK * block bytes), or GGQ_E_* (<0). */
 int64_t ggq_packed_nbytes(int fmt, int64_t O, int64_t K);
 

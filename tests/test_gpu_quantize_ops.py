@@ -60,3 +60,21 @@ def test_reference_style_pipeline_on_gpu():
     ref = orc.ref32("q8_0", A.cpu().numpy(), X.cpu().numpy(), M, N, K)
     mx, fro = orc.tier1_errors(C.float().cpu().numpy(), ref)
     assert mx <= orc.TIER1_MAX and fro <= orc.TIER1_FRO
+
+
+@pytest.mark.parametrize("fmt", ("q8_0", "q4_k", "q6_k"))
+def test_reference_arithmetic_mode_is_bit_identical(golden, fmt):
+    """GPU Q8_1 mode == the reference's kernels/cpu_impls outputs (golden) and == the oracle on fresh inputs."""
+    from kernels import q8_1_mode
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    fn = {"q8_0": q8_1_mode.mmq_q8_0_q8_1, "q4_k": q8_1_mode.mmq_q4_k_q8_1, "q6_k": q8_1_mode.mmq_q6_k_q8_1}[fmt]
+    for c in golden[fmt]:
+        got = fn(torch.from_numpy(c["A"]).cuda(), torch.from_numpy(c["B"]).cuda(), c["M"], c["N"], c["K"]).cpu().numpy()
+        assert np.array_equal(got.view(np.uint16), np.ascontiguousarray(c["C"]).view(np.uint16)), (fmt, c["M"], c["N"], c["K"])
+    M, N, K = 48, 5, 2048
+    A = orc.random_blocks(fmt, M, K, seed=8)
+    X = np.random.default_rng(9).standard_normal((N, K)).astype(np.float16)
+    Bq = quantize_to_q8_1(torch.from_numpy(X).cuda())               # GPU packer feeding the GPU parity kernel
+    got = fn(torch.from_numpy(A).cuda(), Bq, M, N, K).cpu().numpy()
+    want = np.ascontiguousarray(orc.mmq_cpu(fmt, A, X, M, N, K))
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
