@@ -18,6 +18,7 @@
 //   AT  tiles whose accumulators a warp keeps live while the CTA walks the K-slices (4 when the
 //       activations of all tokens do not fit in shared memory at once, else 1)
 // HBM traffic = packed weight bytes once (+ <= 3 % activations/outputs); roofline: HBM bandwidth.
+#include <cstring>
 #include <algorithm>
 #include <cstdlib>
 
@@ -32,7 +33,7 @@ namespace ggq {
 namespace dec {
 
 constexpr int MAX_NW = 16;                // most warps per CTA of any configuration
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
 constexpr int SMEM_LIMIT_2 = 113 * 1024;  // per CTA when two CTAs share an SM (228 KB - 2 x 1 KB reserved)
 
@@ -56,9 +57,11 @@ struct Params {
 };
 
 // NW warps per CTA, MINB CTAs per SM (register budget), NT 8-token n-tiles, AT live tiles per warp
-template <int FMT, int NT, int AT, int NW, int MINB>
+// GV: single-token (GEMV) tile code, see decode_tile.cuh
+template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
+    static_assert(!GV || (NT == 1 && AT == 1), "the GEMV tile code is single-token, one live tile");
     using G = Geo<FMT>;
     constexpr int SUBTILES = G::CHUNK_BLOCKS / G::PREP_BLOCKS;  // TMA boxes per stage
     constexpr int STAGE_BYTES = SUBTILES * 16 * G::SLOT;
@@ -86,122 +89,9 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 
     const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
     // live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA
-    auto tile_of = [&](int batch, int a) -> int64_t {
-        return (static_cast<int64_t>(batch * AT + a) * gridDim.x + blockIdx.x) * WT + tg;
-    };
-    auto slice_chunks = [&](int slice) { return min(p.cps, p.nc - slice * p.cps); };
-
-    // ---- producer cursor: walks exactly the item sequence the consumer loops below walk ----------
-    struct Cur {
-        int batch, slice, a, ci;
-        bool done;
-    };
-    auto normalize = [&](Cur& c) {
-        while (true) {
-            if (c.batch >= p.num_batches) { c.done = true; return; }
-            if (c.slice >= p.n_slices) { c.slice = 0; c.a = 0; c.ci = sub; ++c.batch; continue; }
-            if (c.a >= AT) { c.a = 0; c.ci = sub; ++c.slice; continue; }
-            if (tile_of(c.batch, c.a) >= p.num_tiles || c.ci >= slice_chunks(c.slice)) { ++c.a; c.ci = sub; continue; }
-            return;
-        }
-    };
-    auto issue = [&](const Cur& c, int stage) {
-        const int64_t row0 = tile_of(c.batch, c.a) * 16;
-        const int chunk = c.slice * p.cps + c.ci;
-        const int b0 = chunk * G::CHUNK_BLOCKS;
-        const int goff = b0 * G::BLK;
-        uint64_t* bar = my_full + stage;
-        if (lane == 0) {  // 2-D TMA boxes of 16 rows x SLOT bytes of the raw packed rows, each starting at the 16-byte
-                          // aligned superset of its blocks; rows >= O and bytes past the row end are zero-filled
-            mbar_arrive_expect_tx(bar, STAGE_BYTES);
-#pragma unroll
-            for (int sub = 0; sub < SUBTILES; ++sub)
-                tma_load_2d(ring + stage * STAGE_BYTES + sub * 16 * G::SLOT, &map_w,
-                            ((goff + sub * G::PREP_BLOCKS * G::BLK) & ~15) >> 2, static_cast<int>(row0), bar);
-        }
-    };
-
-    Cur pc{0, 0, 0, sub, false};
-    normalize(pc);
-    for (int s = 0; s < STG && !pc.done; ++s) {
-        issue(pc, s);
-        pc.ci += KW;
-        normalize(pc);
-    }
-
-    uint32_t full_phase = 0, x_phase = 0;
-    int cstage = 0;
-    const int tok0 = min(L.g, p.T - 1), tok1 = min(8 + L.g, p.T - 1);
-
-    for (int batch = 0; batch < p.num_batches; ++batch) {
-        Acc<NT> acc[AT];
-#pragma unroll
-        for (int a = 0; a < AT; ++a)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[a].v[nt][i] = 0.f;
-
-        for (int slice = 0; slice < p.n_slices; ++slice) {
-            const int nsc = slice_chunks(slice);
-            if (p.n_slices > 1 || batch == 0) {
-                // ---- stage this K-slice of the activations + its block-sum table ----------------
-                const int e0 = slice * p.cps * G::CHUNK_ELEMS;
-                const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
-                __syncthreads();  // every warp is done with the previous slice's x / tbl
-                if (tid == 0) {
-                    if (p.sync.world > 0 && p.sync.x_ready != nullptr && batch == 0 && slice == 0) {
-                        // activations are produced by rank 0 (peer memory): wait for its "ready" word of this step
-                        while (ld_acquire_sys(p.sync.x_ready) < p.sync.epoch) {
-                        }
-                        fence_proxy_async_all();  // the TMA engine (async proxy) reads what we just acquired
-                    }
-                    mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
-                    for (int t = 0; t < p.T; ++t)
-                        bulk_g2s(xs + t * p.x_stride, p.X + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
-                                 static_cast<uint32_t>(ne * 2), &bars[0]);
-                }
-                mbar_wait(&bars[0], x_phase);
-                x_phase ^= 1;
-                stage_activations<FMT, NT>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
-                __syncthreads();
-            }
-#pragma unroll
-            for (int a = 0; a < AT; ++a) {
-                if (tile_of(batch, a) >= p.num_tiles) continue;  // warp-uniform
-                for (int ci = sub; ci < nsc; ci += KW) {
-                    mbar_wait(my_full + cstage, (full_phase >> cstage) & 1u);
-                    full_phase ^= 1u << cstage;
-                    const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
-                    const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
-                    StageArgs s;
-                    s.xrow[0] = xs + tok0 * p.x_stride;
-                    s.xrow[1] = xs + tok1 * p.x_stride;
-                    s.xv[0] = L.g < p.T;
-                    s.xv[1] = 8 + L.g < p.T;
-                    s.tbl = tbl;
-                    s.scratch = scr;
-                    for (int b = 0; b < nblk && !p.dbg_skip_compute; b += G::PREP_BLOCKS) {
-                        s.rows = ring + cstage * STAGE_BYTES + (b / G::PREP_BLOCKS) * 16 * G::SLOT;
-                        s.data_off = (b0 * G::BLK) & 15;
-                        s.nblk = min(G::PREP_BLOCKS, nblk - b);
-                        s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
-                        Tile<FMT, NT>::prep(L, s);
-                        __syncwarp();
-                        Tile<FMT, NT>::compute(L, s, acc[a]);
-                        __syncwarp();  // all lanes are done reading the stage and the scratch
-                    }
-                    if (!pc.done) {
-                        issue(pc, cstage);
-                        pc.ci += KW;
-                        normalize(pc);
-                    }
-                    cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
-                }
-            }
-        }
-
-        // ---- epilogue: (reduce over the KW warps of a tile,) round to fp16, store -----------------
+    // ---- epilogue of one batch: (reduce over the KW warps of a tile,) round to fp16, store ------------
+    auto epilogue = [&](Acc<NT>* acc, int batch) {
+        if constexpr (GV) gemv_finalize(acc[0]);
         if (KW > 1) {
 #pragma unroll
             for (int a = 0; a < AT; ++a) {
@@ -223,25 +113,185 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 }
             }
         }
-        if (sub == 0) {
+        if (sub != 0) return;
 #pragma unroll
-            for (int a = 0; a < AT; ++a) {
-                const int64_t tile = tile_of(batch, a);
-                if (tile >= p.num_tiles) continue;
+        for (int a = 0; a < AT; ++a) {
+            const int tile = ((batch * AT + a) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * WT + tg;
+            if (tile >= p.num_tiles) continue;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (GV && (i & 1)) continue;  // single token: column 0 only
+                    const int64_t row = static_cast<int64_t>(tile) * 16 + L.g + ((i & 2) ? 8 : 0);
+                    const int col = 8 * nt + 2 * L.t + (i & 1);
+                    if (row < p.O && col < p.T) {
+                        const __half h = __float2half_rn(acc[a].v[nt][i]);
+                        const int64_t at = col * p.ldc + row;
+                        p.outs.p[0][at] = h;
+                        for (int o = 1; o < p.outs.n; ++o) p.outs.p[o][at] = h;
+                    }
+                }
+        }
+    };
+
+    const bool skip_math = p.dbg_skip_compute != 0;
+    const int tok0 = min(L.g, p.T - 1), tok1 = min(8 + L.g, p.T - 1);
+    uint32_t full_phase = 0, x_phase = 0;
+    int cstage = 0;
+
+    // ---- stage one K-slice of the activations + its block-sum table (all threads) -------------------
+    auto stage_x = [&](int slice, bool first) {
+        const int e0 = slice * p.cps * G::CHUNK_ELEMS;
+        const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
+        __syncthreads();  // every warp is done with the previous slice's x / tbl
+        if (tid == 0) {
+            if (p.sync.world > 0 && p.sync.x_ready != nullptr && first) {
+                // activations are produced by rank 0 (peer memory): wait for its "ready" word of this step
+                while (ld_acquire_sys(p.sync.x_ready) < p.sync.epoch) {
+                }
+                fence_proxy_async_all();  // the TMA engine (async proxy) reads what we just acquired
+            }
+            mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
+            for (int t = 0; t < p.T; ++t)
+                bulk_g2s(xs + t * p.x_stride, p.X + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
+                         static_cast<uint32_t>(ne * 2), &bars[0]);
+        }
+        mbar_wait(&bars[0], x_phase);
+        x_phase ^= 1;
+        stage_activations<FMT, NT, GV>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
+        __syncthreads();
+    };
+
+    // ---- consume the chunk sitting in ring stage `cstage` (chunk `ci` of K-slice `slice`) -----------
+    auto consume = [&](int slice, int ci, Acc<NT>& acc) {
+        mbar_wait(my_full + cstage, (full_phase >> cstage) & 1u);
+        full_phase ^= 1u << cstage;
+        const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
+        const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
+        StageArgs s;
+        s.xrow[0] = xs + tok0 * p.x_stride;
+        s.xrow[1] = xs + tok1 * p.x_stride;
+        s.xv[0] = L.g < p.T;
+        s.xv[1] = 8 + L.g < p.T;
+        s.tbl = tbl;
+        s.scratch = scr;
+        s.data_off = (b0 * G::BLK) & 15;
+        if (!skip_math) {
+#pragma unroll
+            for (int u = 0; u < SUBTILES; ++u) {
+                const int b = u * G::PREP_BLOCKS;
+                if (b < nblk) {
+                    s.rows = ring + cstage * STAGE_BYTES + u * 16 * G::SLOT;
+                    s.nblk = min(G::PREP_BLOCKS, nblk - b);
+                    s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
+                    Tile<FMT, NT, GV>::prep(L, s);
+                    __syncwarp();
+                    Tile<FMT, NT, GV>::compute(L, s, acc);
+                    __syncwarp();  // all lanes are done reading the stage and the scratch
+                }
+            }
+        }
+    };
+    // one elected lane: the 2-D TMA boxes (16 rows x SLOT bytes of the raw packed rows, each starting at the 16-byte
+    // aligned superset of its blocks; rows >= O and bytes past the row end are zero-filled) of chunk `chunk` of the
+    // tile whose first row is `row0`, into ring stage `stage`
+    auto issue_boxes = [&](int row0, int chunk, int stage) {
+        if (lane == 0) {
+            const int goff = chunk * (G::CHUNK_BLOCKS * G::BLK);
+            uint64_t* bar = my_full + stage;
+            mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+            for (int u = 0; u < SUBTILES; ++u)
+                tma_load_2d(ring + stage * STAGE_BYTES + u * 16 * G::SLOT, &map_w,
+                            ((goff + u * G::PREP_BLOCKS * G::BLK) & ~15) >> 2, row0, bar);
+        }
+    };
+
+    if constexpr (AT == 1) {
+        // ======== single K-slice (the plan has AT == 1 exactly then): a flat walk over (tile, chunk) ========
+        const int tstride = static_cast<int>(gridDim.x) * WT;
+        const int tile0 = static_cast<int>(blockIdx.x) * WT + tg;
+        int ptile = tile0, pci = sub;                     // producer cursor, STG items ahead of the consumer
+        bool pdone = ptile >= p.num_tiles || sub >= p.nc;
+        auto produce = [&](int stage) {
+            issue_boxes(ptile * 16, pci, stage);
+            pci += KW;
+            if (pci >= p.nc) {
+                pci = sub;
+                ptile += tstride;
+                pdone = ptile >= p.num_tiles;
+            }
+        };
+        for (int s = 0; s < STG && !pdone; ++s) produce(s);
+        stage_x(0, true);
+
+        for (int batch = 0, tile = tile0; batch < p.num_batches; ++batch, tile += tstride) {
+            Acc<NT> acc[1];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[0].v[nt][i] = 0.f;
+            if (tile < p.num_tiles) {  // warp-uniform
+                for (int ci = sub; ci < p.nc; ci += KW) {
+                    consume(0, ci, acc[0]);
+                    if (!pdone) produce(cstage);
+                    cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+                }
+            }
+            epilogue(acc, batch);
+        }
+    } else {
+        // ======== K-sliced walk: AT live tiles per warp share each staged activation slice ========
+        auto tile_of = [&](int batch, int a) -> int64_t {
+            return (static_cast<int64_t>(batch * AT + a) * gridDim.x + blockIdx.x) * WT + tg;
+        };
+        auto slice_chunks = [&](int slice) { return min(p.cps, p.nc - slice * p.cps); };
+        // producer cursor: walks exactly the item sequence the consumer loops below walk
+        struct Cur {
+            int batch, slice, a, ci;
+            bool done;
+        };
+        auto normalize = [&](Cur& c) {
+            while (true) {
+                if (c.batch >= p.num_batches) { c.done = true; return; }
+                if (c.slice >= p.n_slices) { c.slice = 0; c.a = 0; c.ci = sub; ++c.batch; continue; }
+                if (c.a >= AT) { c.a = 0; c.ci = sub; ++c.slice; continue; }
+                if (tile_of(c.batch, c.a) >= p.num_tiles || c.ci >= slice_chunks(c.slice)) { ++c.a; c.ci = sub; continue; }
+                return;
+            }
+        };
+        Cur pc{0, 0, 0, sub, false};
+        normalize(pc);
+        auto produce = [&](int stage) {
+            issue_boxes(static_cast<int>(tile_of(pc.batch, pc.a) * 16), pc.slice * p.cps + pc.ci, stage);
+            pc.ci += KW;
+            normalize(pc);
+        };
+        for (int s = 0; s < STG && !pc.done; ++s) produce(s);
+
+        for (int batch = 0; batch < p.num_batches; ++batch) {
+            Acc<NT> acc[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int64_t row = tile * 16 + L.g + ((i & 2) ? 8 : 0);
-                        const int col = 8 * nt + 2 * L.t + (i & 1);
-                        if (row < p.O && col < p.T) {
-                            const __half h = __float2half_rn(acc[a].v[nt][i]);
+                    for (int i = 0; i < 4; ++i) acc[a].v[nt][i] = 0.f;
+            for (int slice = 0; slice < p.n_slices; ++slice) {
+                const int nsc = slice_chunks(slice);
+                stage_x(slice, batch == 0 && slice == 0);
 #pragma unroll
-                            for (int o = 0; o < 8; ++o)
-                                if (o < p.outs.n) p.outs.p[o][col * p.ldc + row] = h;
-                        }
+                for (int a = 0; a < AT; ++a) {
+                    if (tile_of(batch, a) >= p.num_tiles) continue;  // warp-uniform
+                    for (int ci = sub; ci < nsc; ci += KW) {
+                        consume(slice, ci, acc[a]);
+                        if (!pc.done) produce(cstage);
+                        cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
                     }
+                }
             }
+            epilogue(acc, batch);
         }
     }
 
@@ -361,19 +411,24 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     return true;
 }
 
-// Preference order: two 8-warp CTAs per SM (16 resident warps hide the shared-memory latency of the
-// unpack -> MMA -> scale chains) when the whole problem state fits in half an SM's shared memory,
-// else one CTA per SM with the full 227 KB (activations of many tokens / K-slicing).
+// Preference order (measured on B200, profiles/README.md): 12 warps with >= 3 ring stages each; else two 8-warp
+// CTAs per SM (16 resident warps, 2 stages) when the problem state fits in half an SM's shared memory; else one
+// CTA per SM with the full 227 KB (activations of many tokens / K-slicing).
 template <int FMT>
 static bool make_plan(const MmArgs& a, int T, Plan& pl) {
+    if (const char* f = getenv("GGQ_PLAN_FORCE")) {  // dev: "8,2" | "12,1" | "8,1"
+        const int nw = atoi(f), occ = (strchr(f, ',') ? atoi(strchr(f, ',') + 1) : 1);
+        return make_plan_cfg<FMT>(a, T, nw, occ, nw == 8 && occ == 1, pl);
+    }
+    if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 3) return true;
     if (make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 2) return true;
     return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
 }
 
-template <int FMT, int NT, int AT, int NW, int MINB>
+template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false>
 static int launch_kernel(const Plan& pl, cudaStream_t stream) {
-    auto kern = decode_kernel<FMT, NT, AT, NW, MINB>;
+    auto kern = decode_kernel<FMT, NT, AT, NW, MINB, GV>;
     static int configured_dev_mask[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -405,7 +460,11 @@ static int launch_fmt(const MmArgs& a) {
         Plan pl;
         if (!make_plan<FMT>(s, T, pl)) return GGQ_E_FAMILY;
         int rc;
-        if (pl.occ == 2) {  // AT == 1 by construction
+        if (T == 1 && pl.at == 1 && pl.p.n_slices == 1 && !getenv("GGQ_NO_GEMV")) {  // single token: GEMV tile code
+            rc = pl.occ == 2   ? launch_kernel<FMT, 1, 1, 8, 2, true>(pl, a.stream)
+                 : pl.nw == 12 ? launch_kernel<FMT, 1, 1, 12, 1, true>(pl, a.stream)
+                               : launch_kernel<FMT, 1, 1, 8, 1, true>(pl, a.stream);
+        } else if (pl.occ == 2) {  // AT == 1 by construction
             rc = pl.nt == 1 ? launch_kernel<FMT, 1, 1, 8, 2>(pl, a.stream) : launch_kernel<FMT, 2, 1, 8, 2>(pl, a.stream);
         } else if (pl.nw == 12) {
             rc = pl.nt == 1 ? launch_kernel<FMT, 1, 1, 12, 1>(pl, a.stream) : launch_kernel<FMT, 2, 1, 12, 1>(pl, a.stream);

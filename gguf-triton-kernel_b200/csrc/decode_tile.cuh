@@ -35,6 +35,7 @@ GGQ_DEV uint32_t funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return _
 GGQ_DEV float h2f(uint32_t bits) { return __half2float(__ushort_as_half(static_cast<unsigned short>(bits))); }
 GGQ_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
 GGQ_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
+GGQ_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GGQ_DEV void mma16816_bf16(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[4]) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
@@ -73,9 +74,14 @@ template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B in one TMA
     static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
     static constexpr float TBL_MUL = -128.f / 16777216.f;   // cancels the +128 of (q ^ 0x80)
 };
-template <> struct Geo<1> {  // Q4_K: 4 blocks = 1024 weights = 576 B, two TMA boxes of 2 blocks (288 B pitch: rows land 8 banks
-                             // apart, so the lanes' 64-bit loads are conflict free)
-    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576, SLOT = 288;
+template <> struct Geo<1> {  // Q4_K: 2 blocks = 512 weights = 288 B = one TMA box per stage (288 B pitch: rows land 8 banks apart, so
+                             // the lanes' 64-bit loads are conflict free).  Small stages let 12-16 warps per SM keep >= 2 stages
+                             // each; 4-block stages with 8 warps measured slower once the per-chunk control code was trimmed.
+#ifndef GGQ_Q4K_CHUNK
+#define GGQ_Q4K_CHUNK 2
+#endif
+    static constexpr int QK = 256, BLK = 144, CHUNK_BLOCKS = GGQ_Q4K_CHUNK, CHUNK_ELEMS = 256 * CHUNK_BLOCKS,
+                         CHUNK_BYTES = 144 * CHUNK_BLOCKS, SLOT = 288;
     static constexpr int PREP_BLOCKS = 2;
     static constexpr int GROUP = 32;
     static constexpr int SCRATCH_PER_BLOCK = 80;  // 64 B payload + 16 B pad: rows 20 banks apart
@@ -111,6 +117,17 @@ GGQ_DEV uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_
 GGQ_DEV uint32_t ld32p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint32_t*>(p) : 0u; }
 GGQ_DEV uint2 ld64p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint2*>(p) : uint2{0u, 0u}; }
 GGQ_DEV uint4 ld128p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<const uint4*>(p) : uint4{0u, 0u, 0u, 0u}; }
+// Predicated shared-memory load that KEEPS the destination of inactive lanes (no zeroing): the lanes whose token does
+// not exist feed MMA columns that are never stored, so whatever they hold is fine.
+GGQ_DEV void ld128k(uint4& d, const uint8_t* p, bool v) {
+#if defined(__CUDACC__) && defined(GGQ_XLOAD_ASM)
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n}\n"
+                 : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w)
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(static_cast<int>(v)));
+#else
+    if (v) d = *reinterpret_cast<const uint4*>(p);
+#endif
+}
 GGQ_DEV uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
 GGQ_DEV uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 GGQ_DEV float4 ld128f(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
@@ -201,6 +218,73 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             acc.v[nt][3] = fmaf(db_o, d[3], acc.v[nt][3]);
         }
     }
+}
+
+
+// ---- Q8_0, one token (GEMV): the 8 MMA columns carry 8 consecutive blocks (see the Q4_K GEMV notes below) ----
+// Lane (g, t) loads the activations of block g of the 8-block group in the pattern of that block's parity (even
+// blocks: k = 2 + 4t.., odd blocks: k = 4t..) once per group; column j of block j's MMAs is the dot product, held by
+// lane t == j / 2, which also is the only lane that converts that block's scale.
+GGQ_DEV void compute_q8_0_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
+    using G = Geo<0>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    const uint32_t wrap_sel = (L.t == 3) ? 0x7610u : 0x3210u;
+    const int t4 = 4 * L.t;
+    const bool even = !(L.g & 1);
+    const int o1 = even ? 2 + t4 : t4, o3 = o1 + 16, o4 = (o3 + 2) & 31;
+    float a0 = acc.v[0][0], a1 = acc.v[0][1], a2 = acc.v[0][2], a3 = acc.v[0][3];
+#pragma unroll
+    for (int u = 0; u < G::PREP_BLOCKS / 8; ++u) {
+        if (8 * u >= s.nblk) break;
+        const int kb8 = s.k0 + 256 * u;
+        const uint8_t* x = s.xrow[0] + 2 * (kb8 + 32 * L.g);
+        const uint32_t b1[2] = {ld32(x + 2 * o1), ld32(x + 2 * (o1 + 2))};
+        const uint32_t b2[2] = {ld32(x + 2 * o3), ld32(x + 2 * o4)};
+        const float2 tb = ld64f(s.tbl + (kb8 >> 5) + 2 * L.t);
+        const float c[4] = {tb.x, tb.y, tb.x, tb.y};
+        // this lane's scales: the pair of blocks (2t, 2t + 1) of the group, rows g and g + 8
+        const uint8_t* da = r0 + 68 * (4 * u + L.t);
+        const uint8_t* db = r1 + 68 * (4 * u + L.t);
+        const float sa_e = h2f(ld16(da)) * 16777216.f, sa_o = h2f(ld16(da + 34)) * 16777216.f;
+        const float sb_e = h2f(ld16(db)) * 16777216.f, sb_o = h2f(ld16(db + 34)) * 16777216.f;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const uint8_t* a = r0 + 68 * (4 * u + pp);
+            const uint8_t* b = r1 + 68 * (4 * u + pp);
+            const uint32_t a0w = ld32(a), b0w = ld32(b);
+            uint32_t ae1 = ld32(a + 4 + t4), ae2 = ld32(a + 20 + t4), ao1 = ld32(a + 36 + t4), ao2 = ld32(a + 52 + t4);
+            uint32_t be1 = ld32(b + 4 + t4), be2 = ld32(b + 20 + t4), bo1 = ld32(b + 36 + t4), bo2 = ld32(b + 52 + t4);
+            ae2 = prmt(ae2, a0w, wrap_sel);
+            be2 = prmt(be2, b0w, wrap_sel);
+            uint32_t fa[4], fb[4];
+            float d[4];
+            q8_to_h2(ae1, fa[0], fa[2]);
+            q8_to_h2(be1, fa[1], fa[3]);
+            q8_to_h2(ae2, fb[0], fb[2]);
+            q8_to_h2(be2, fb[1], fb[3]);
+            mma16816(d, fa, b1, c);
+            mma16816(d, fb, b2, d);
+            if (L.t == pp) {
+                a0 = fmaf(sa_e, d[0], a0);
+                a2 = fmaf(sb_e, d[2], a2);
+            }
+            q8_to_h2(ao1, fa[0], fa[2]);
+            q8_to_h2(bo1, fa[1], fa[3]);
+            q8_to_h2(ao2, fb[0], fb[2]);
+            q8_to_h2(bo2, fb[1], fb[3]);
+            mma16816(d, fa, b1, c);
+            mma16816(d, fb, b2, d);
+            if (L.t == pp) {
+                a1 = fmaf(sa_o, d[1], a1);
+                a3 = fmaf(sb_o, d[3], a3);
+            }
+        }
+    }
+    acc.v[0][0] = a0;
+    acc.v[0][1] = a1;
+    acc.v[0][2] = a2;
+    acc.v[0][3] = a3;
 }
 
 // =============================================================================================
@@ -311,6 +395,11 @@ GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) 
     const uint8_t* r1 = r0 + 8 * G::SLOT;
     const float zero[4] = {0.f, 0.f, 0.f, 0.f};
     const uint2* xbt = reinterpret_cast<const uint2*>(s.tbl);
+    uint4 xek[2][NT], xok[2][NT];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) xek[j][nt] = xok[j][nt] = uint4{0u, 0u, 0u, 0u};
 #pragma unroll
     for (int i = 0; i < G::PREP_BLOCKS; ++i) {
         if (!FULL && i >= s.nblk) break;
@@ -353,8 +442,10 @@ GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) 
             const int kb = s.k0 + 256 * i + 64 * c;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint4 xe = ld128p(s.xrow[nt] + 2 * (kb + 8 * L.t), s.xv[nt]);   // permuted: (x0 x2 | x1 x3 | x4 x6 | x5 x7)
-                const uint4 xo = ld128p(s.xrow[nt] + 2 * (kb + 32 + 8 * L.t), s.xv[nt]);
+                uint4& xe = xek[c & 1][nt];
+                uint4& xo = xok[c & 1][nt];
+                ld128k(xe, s.xrow[nt] + 2 * (kb + 8 * L.t), s.xv[nt]);   // permuted: (x0 x2 | x1 x3 | x4 x6 | x5 x7)
+                ld128k(xo, s.xrow[nt] + 2 * (kb + 32 + 8 * L.t), s.xv[nt]);
                 float de[4], dd[4];
                 uint32_t bf[2] = {xe.x, xe.y};
                 mma16816(de, e1f, bf, zero);
@@ -389,6 +480,159 @@ template <int NT>
 GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     if (s.nblk == Geo<1>::PREP_BLOCKS) compute_q4_k_impl<NT, true>(L, s, acc);
     else compute_q4_k_impl<NT, false>(L, s, acc);
+}
+
+
+// ---- Q4_K, one token (GEMV) ----------------------------------------------------------------------
+// With a single token only column 0 of the m16n8 MMA would carry data.  Instead the 8 columns carry the 8 sub-blocks
+// of a block: lane (g, t) loads the activations of sub-block g (its t-th quarter) ONCE per block and uses them as the
+// B fragment of all 16 MMAs of the block, so D_j[row, n] = <weights of sub-block j, activations of sub-block n>.
+// Only the column n == j is meaningful; it lives in lane t == j / 2, which applies the sub-block scale with a
+// predicated FMA.  Per block and lane: 1 activation load (instead of 8), 2 scale loads (instead of 8), 20 FMAs
+// (instead of 36) and no min-term MMA: -dmin * m_j * sum_j(x) is one more FMA per (row, sub-block).  The four
+// accumulators of a lane are partial sums over (row g / g + 8) x (even / odd sub-blocks); gemv_finalize() folds
+// them over the quad.
+// prep: scratch entry = 64 B per (row, block): four 16-byte pieces {s_2t, s_2t+1, -dmin*m_2t, -dmin*m_2t+1},
+// piece t stored at position t ^ ((row >> 1) & 3) so that both the 128-bit stores of prep (lane = row) and the
+// 128-bit loads of compute (lane = (g, t)) are bank-conflict free.
+GGQ_DEV void prep_q4_k_gv(const Lane& L, const StageArgs& s) {
+    using G = Geo<1>;
+    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+        const int row = p & 15, blk = p >> 4;
+        const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
+        const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
+        const uint32_t u0 = h.y, u1 = h.z, u2 = h.w;
+        const uint32_t sc_lo = u0 & 0x3f3f3f3fu, m_lo = u1 & 0x3f3f3f3fu;
+        const uint32_t sc_hi = (u2 & 0x0f0f0f0fu) | ((u0 >> 2) & 0x30303030u);
+        const uint32_t m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | ((u1 >> 2) & 0x30303030u);
+        // (2^23 + n) * c - 2^23 * c == n * c exactly (one rounding, n * c has <= 17 significant bits)
+        const float d24 = d * 16777216.f, d20 = d * 1048576.f;
+        const float n24 = d24 * -8388608.f, n20 = d20 * -8388608.f;
+        const float dm = -dmin, ndm = dmin * 8388608.f;
+        float4 c0, c1, c2, c3;
+        c0.x = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7650)), d24, n24);
+        c0.y = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7651)), d20, n20);
+        c1.x = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7652)), d24, n24);
+        c1.y = fmaf(u2f(prmt(sc_lo, 0x4B000000u, 0x7653)), d20, n20);
+        c2.x = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7650)), d24, n24);
+        c2.y = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7651)), d20, n20);
+        c3.x = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7652)), d24, n24);
+        c3.y = fmaf(u2f(prmt(sc_hi, 0x4B000000u, 0x7653)), d20, n20);
+        c0.z = fmaf(u2f(prmt(m_lo, 0x4B000000u, 0x7650)), dm, ndm);
+        c0.w = fmaf(u2f(prmt(m_lo, 0x4B000000u, 0x7651)), dm, ndm);
+        c1.z = fmaf(u2f(prmt(m_lo, 0x4B000000u, 0x7652)), dm, ndm);
+        c1.w = fmaf(u2f(prmt(m_lo, 0x4B000000u, 0x7653)), dm, ndm);
+        c2.z = fmaf(u2f(prmt(m_hi, 0x4B000000u, 0x7650)), dm, ndm);
+        c2.w = fmaf(u2f(prmt(m_hi, 0x4B000000u, 0x7651)), dm, ndm);
+        c3.z = fmaf(u2f(prmt(m_hi, 0x4B000000u, 0x7652)), dm, ndm);
+        c3.w = fmaf(u2f(prmt(m_hi, 0x4B000000u, 0x7653)), dm, ndm);
+        uint8_t* e = s.scratch + (blk * 16 + row) * 64;
+        const int sw = ((row >> 1) & 3) << 4;
+        *reinterpret_cast<float4*>(e + sw) = c0;
+        *reinterpret_cast<float4*>(e + (sw ^ 16)) = c1;
+        *reinterpret_cast<float4*>(e + (sw ^ 32)) = c2;
+        *reinterpret_cast<float4*>(e + (sw ^ 48)) = c3;
+    }
+}
+
+// staging for the GEMV kernel: permute 64 activations in place (as q4k_stage_pair) and write the two fp32 sums
+GGQ_DEV void q4k_stage_pair_gv(uint8_t* x, float* sums2) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float sum = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            uint4* ptr = reinterpret_cast<uint4*>(x + 64 * j + 16 * v);
+            const uint4 q = *ptr;
+            sum += h2f(q.x & 0xffffu);
+            sum += h2f(q.x >> 16);
+            sum += h2f(q.y & 0xffffu);
+            sum += h2f(q.y >> 16);
+            sum += h2f(q.z & 0xffffu);
+            sum += h2f(q.z >> 16);
+            sum += h2f(q.w & 0xffffu);
+            sum += h2f(q.w >> 16);
+            uint4 o;
+            o.x = prmt(q.x, q.y, 0x5410);
+            o.y = prmt(q.x, q.y, 0x7632);
+            o.z = prmt(q.z, q.w, 0x5410);
+            o.w = prmt(q.z, q.w, 0x7632);
+            *ptr = o;
+        }
+        sums2[j] = sum;
+    }
+}
+
+template <bool FULL>
+GGQ_DEV void compute_q4_k_gv_impl(const Lane& L, const StageArgs& s, Acc<1>& acc) {
+    using G = Geo<1>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    const int piece = (L.t ^ ((L.g >> 1) & 3)) << 4;
+    float a0 = acc.v[0][0], a1 = acc.v[0][1], a2 = acc.v[0][2], a3 = acc.v[0][3];
+#pragma unroll
+    for (int i = 0; i < G::PREP_BLOCKS; ++i) {
+        if (!FULL && i >= s.nblk) break;
+        const uint8_t* q0 = r0 + i * G::BLK + 16 + 8 * L.t;
+        const uint8_t* q1 = r1 + i * G::BLK + 16 + 8 * L.t;
+        const uint8_t* e0 = s.scratch + (i * 16 + L.g) * 64 + piece;
+        const float4 ca = ld128f(e0), cb = ld128f(e0 + 8 * 64);
+        const int kb = s.k0 + 256 * i;
+        const float2 sm = ld64f(s.tbl + (kb >> 5) + 2 * L.t);                 // sums of sub-blocks 2t, 2t+1
+        const uint4 xr = ld128(s.xrow[0] + 2 * (kb + 32 * L.g + 8 * L.t));  // sub-block g, quarter t (permuted)
+        const uint32_t b1[2] = {xr.x, xr.y}, b2[2] = {xr.z, xr.w};
+        a0 = fmaf(ca.z, sm.x, a0);
+        a1 = fmaf(ca.w, sm.y, a1);
+        a2 = fmaf(cb.z, sm.x, a2);
+        a3 = fmaf(cb.w, sm.y, a3);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
+            uint32_t e1f[4], e2f[4], o1f[4], o2f[4];
+            e1f[0] = wa.x & 0x000F000Fu;  e1f[2] = (wa.x >> 8) & 0x000F000Fu;
+            o1f[0] = wa.x & 0x00F000F0u;  o1f[2] = (wa.x >> 8) & 0x00F000F0u;
+            e1f[1] = wb.x & 0x000F000Fu;  e1f[3] = (wb.x >> 8) & 0x000F000Fu;
+            o1f[1] = wb.x & 0x00F000F0u;  o1f[3] = (wb.x >> 8) & 0x00F000F0u;
+            e2f[0] = wa.y & 0x000F000Fu;  e2f[2] = (wa.y >> 8) & 0x000F000Fu;
+            o2f[0] = wa.y & 0x00F000F0u;  o2f[2] = (wa.y >> 8) & 0x00F000F0u;
+            e2f[1] = wb.y & 0x000F000Fu;  e2f[3] = (wb.y >> 8) & 0x000F000Fu;
+            o2f[1] = wb.y & 0x00F000F0u;  o2f[3] = (wb.y >> 8) & 0x00F000F0u;
+            float de[4], dd[4];
+            mma16816(de, e1f, b1, zero);
+            mma16816(de, e2f, b2, de);
+            mma16816(dd, o1f, b1, zero);
+            mma16816(dd, o2f, b2, dd);
+            if (L.t == c) {  // columns 2c (sub-block 2c) and 2c + 1 live in this lane
+                a0 = fmaf(ca.x, de[0], a0);
+                a2 = fmaf(cb.x, de[2], a2);
+                a1 = fmaf(ca.y, dd[1], a1);
+                a3 = fmaf(cb.y, dd[3], a3);
+            }
+        }
+    }
+    acc.v[0][0] = a0;
+    acc.v[0][1] = a1;
+    acc.v[0][2] = a2;
+    acc.v[0][3] = a3;
+}
+
+GGQ_DEV void compute_q4_k_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
+    if (s.nblk == Geo<1>::PREP_BLOCKS) compute_q4_k_gv_impl<true>(L, s, acc);
+    else compute_q4_k_gv_impl<false>(L, s, acc);
+}
+
+// GEMV accumulators -> the standard C-fragment layout (column 0 = the token): v[0] = row g, v[2] = row g + 8
+GGQ_DEV void gemv_finalize(Acc<1>& acc) {
+    float u = acc.v[0][0] + acc.v[0][1], v = acc.v[0][2] + acc.v[0][3];
+    u += shfl_xor(u, 1);
+    v += shfl_xor(v, 1);
+    u += shfl_xor(u, 2);
+    v += shfl_xor(v, 2);
+    acc.v[0][0] = u;
+    acc.v[0][1] = 0.f;
+    acc.v[0][2] = v;
+    acc.v[0][3] = 0.f;
 }
 
 // =============================================================================================
@@ -496,16 +740,135 @@ GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     }
 }
 
+
+// ---- Q6_K, one token (GEMV): the 8 MMA columns carry the 8 sub-blocks (16 weights each) of half a block ----------
+// prep: scratch entry = 64 B per (row, block); piece t = d * 2^24 * {sc[2t], sc[2t+1], sc[8+2t], sc[8+2t+1]} (the four
+// sub-blocks whose column lives in lane t), stored at position t ^ ((row >> 1) & 3) (conflict-free stores and loads).
+GGQ_DEV void prep_q6_k_gv(const Lane& L, const StageArgs& s) {
+    using G = Geo<2>;
+    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+        const int row = p & 15, blk = p >> 4;
+        const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
+        const float d = h2f(ld16(b + 208)) * 16777216.f;
+        // int8 -> fp32 without the integer pipe: byte ^ 0x80 dropped into the mantissa of 2^23; (2^23 + u) - (2^23 + 128)
+        // is exact, and so is the product with d (<= 19 significant bits)
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = (ld16(b + 192 + 4 * k) | (ld16(b + 194 + 4 * k) << 16)) ^ 0x80808080u;
+        float sc[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sc[4 * k + 0] = (u2f(prmt(w[k], 0x4B000000u, 0x7650)) - 8388736.f) * d;
+            sc[4 * k + 1] = (u2f(prmt(w[k], 0x4B000000u, 0x7651)) - 8388736.f) * d;
+            sc[4 * k + 2] = (u2f(prmt(w[k], 0x4B000000u, 0x7652)) - 8388736.f) * d;
+            sc[4 * k + 3] = (u2f(prmt(w[k], 0x4B000000u, 0x7653)) - 8388736.f) * d;
+        }
+        uint8_t* e = s.scratch + (blk * 16 + row) * 64;
+        const int sw = ((row >> 1) & 3) << 4;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float4 v;
+            v.x = sc[2 * t];
+            v.y = sc[2 * t + 1];
+            v.z = sc[8 + 2 * t];
+            v.w = sc[8 + 2 * t + 1];
+            *reinterpret_cast<float4*>(e + (sw ^ (16 * t))) = v;
+        }
+    }
+}
+
+template <bool ODD>
+GGQ_DEV void compute_q6_k_gv_block(const Lane& L, const StageArgs& s, int i, const uint8_t* r0, const uint8_t* r1,
+                                   float& a0, float& a1, float& a2, float& a3) {
+    using G = Geo<2>;
+    const uint8_t* b0 = r0 + i * G::BLK;
+    const uint8_t* b1 = r1 + i * G::BLK;
+    const int piece = (L.t ^ ((L.g >> 1) & 3)) << 4;
+    const uint8_t* e0 = s.scratch + (i * 16 + L.g) * 64 + piece;
+    const float4 sa = ld128f(e0), sb = ld128f(e0 + 8 * 64);
+    const float sca[4] = {sa.x, sa.y, sa.z, sa.w}, scb[4] = {sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int kbh = s.k0 + 256 * i + 128 * h;
+        const uint2 xr = ld64(s.xrow[0] + 2 * (kbh + 16 * L.g + 4 * L.t));  // sub-block g of this half, elements 4t..4t+3
+        const uint32_t bf[2] = {xr.x, xr.y};
+        const float2 tb = ld64f(s.tbl + (kbh >> 4) + 2 * L.t);              // -32 * 2^-24 * sum(x) of sub-blocks 2t, 2t+1
+        const float c[4] = {tb.x, tb.y, tb.x, tb.y};
+#pragma unroll
+        for (int lh = 0; lh < 2; ++lh) {
+            const int l = 16 * lh + 4 * L.t;
+            uint32_t ga[4], gb[4];
+            q6_bytes(ldw<ODD>(b0 + 64 * h + l), ldw<ODD>(b0 + 64 * h + 32 + l), ldw<ODD>(b0 + 128 + 32 * h + l), ga);
+            q6_bytes(ldw<ODD>(b1 + 64 * h + l), ldw<ODD>(b1 + 64 * h + 32 + l), ldw<ODD>(b1 + 128 + 32 * h + l), gb);
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {  // sub-block 8h + 2grp + lh = column 2grp + lh: lane t == grp
+                uint32_t fa[4];
+                fa[0] = prmt(ga[grp], 0u, 0x5140);  // q6 * 2^-24
+                fa[2] = prmt(ga[grp], 0u, 0x7362);
+                fa[1] = prmt(gb[grp], 0u, 0x5140);
+                fa[3] = prmt(gb[grp], 0u, 0x7362);
+                float d[4];
+                mma16816(d, fa, bf, c);
+                if (L.t == grp) {
+                    if (lh == 0) {
+                        a0 = fmaf(sca[2 * h], d[0], a0);
+                        a2 = fmaf(scb[2 * h], d[2], a2);
+                    } else {
+                        a1 = fmaf(sca[2 * h + 1], d[1], a1);
+                        a3 = fmaf(scb[2 * h + 1], d[3], a3);
+                    }
+                }
+            }
+        }
+    }
+}
+
+GGQ_DEV void compute_q6_k_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
+    using G = Geo<2>;
+    const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
+    const uint8_t* r1 = r0 + 8 * G::SLOT;
+    float a0 = acc.v[0][0], a1 = acc.v[0][1], a2 = acc.v[0][2], a3 = acc.v[0][3];
+#pragma unroll
+    for (int i = 0; i < G::PREP_BLOCKS; i += 2) {
+        compute_q6_k_gv_block<false>(L, s, i, r0, r1, a0, a1, a2, a3);
+        compute_q6_k_gv_block<true>(L, s, i + 1, r0, r1, a0, a1, a2, a3);
+    }
+    acc.v[0][0] = a0;
+    acc.v[0][1] = a1;
+    acc.v[0][2] = a2;
+    acc.v[0][3] = a3;
+}
+
 // ---- activation staging pass (after the TMA copies of the K-slice have landed) ------------------
 // Builds the per-slice table every thread block needs next to the raw fp16 rows:
 //   Q8_0 / Q6_K: tbl[j][col] = TBL_MUL * sum of the GROUP activations of group j of token col (fp32)
 //   Q4_K:        the bf16 hi/lo B fragments of the min-term MMA, and permutes the rows in place
 // `ne` activations per token row (multiple of 256 for Q4_K), rows `x_stride` bytes apart.
-template <int FMT, int NT>
+template <int FMT, int NT, bool GV = false>
 GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int ne, int T, int tid, int nthreads) {
     using G = Geo<FMT>;
     constexpr int TPAD = 8 * NT;
-    if (FMT == 1) {
+    if (FMT == 1 && GV) {  // one token: tbl[sub-block] = fp32 sum of its 32 activations
+        for (int e = tid; e < ne / 64; e += nthreads) q4k_stage_pair_gv(xs + e * 128, tbl + 2 * e);
+    } else if (GV) {       // one token: tbl[group] = TBL_MUL * sum of its GROUP activations
+        for (int j = tid; j < ne / G::GROUP; j += nthreads) {
+            const uint8_t* src = xs + j * G::GROUP * 2;
+            float sum = 0.f;
+#pragma unroll
+            for (int v = 0; v < G::GROUP / 8; ++v) {
+                const uint4 q = ld128(src + 16 * v);
+                sum += h2f(q.x & 0xffffu);
+                sum += h2f(q.x >> 16);
+                sum += h2f(q.y & 0xffffu);
+                sum += h2f(q.y >> 16);
+                sum += h2f(q.z & 0xffffu);
+                sum += h2f(q.z >> 16);
+                sum += h2f(q.w & 0xffffu);
+                sum += h2f(q.w >> 16);
+            }
+            tbl[j] = sum * G::TBL_MUL;
+        }
+    } else if (FMT == 1) {
         uint2* xb = reinterpret_cast<uint2*>(tbl);
         const int nent = ne / 64;  // entries per token
         for (int idx = tid; idx < nent * TPAD; idx += nthreads) {
@@ -539,16 +902,28 @@ GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int n
 }
 
 // ---- format dispatch ---------------------------------------------------------------------------
-template <int FMT, int NT> struct Tile;
-template <int NT> struct Tile<0, NT> {
+template <int FMT, int NT, bool GV = false> struct Tile;
+template <> struct Tile<0, 1, true> {
+    static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q8_0_gv(L, s, a); }
+};
+template <> struct Tile<2, 1, true> {
+    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k_gv(L, s); }
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q6_k_gv(L, s, a); }
+};
+template <> struct Tile<1, 1, true> {
+    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k_gv(L, s); }
+    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q4_k_gv(L, s, a); }
+};
+template <int NT> struct Tile<0, NT, false> {
     static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
     static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q8_0<NT>(L, s, a); }
 };
-template <int NT> struct Tile<1, NT> {
+template <int NT> struct Tile<1, NT, false> {
     static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k(L, s); }
     static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q4_k<NT>(L, s, a); }
 };
-template <int NT> struct Tile<2, NT> {
+template <int NT> struct Tile<2, NT, false> {
     static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k(L, s); }
     static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q6_k<NT>(L, s, a); }
 };

@@ -45,6 +45,7 @@ struct WarpEmu {
     std::barrier<> bar{32};
     uint32_t a[32][4];
     uint32_t b[32][2];
+    float x[32];
 };
 inline thread_local WarpEmu* tls_warp = nullptr;
 inline thread_local int tls_lane = 0;
@@ -93,6 +94,14 @@ inline void mma16816_bf16(float d[4], const uint32_t a[4], const uint32_t b[2], 
     w.bar.arrive_and_wait();
 }
 inline void syncwarp() { tls_warp->bar.arrive_and_wait(); }
+inline float shfl_xor(float v, int m) {
+    WarpEmu& w = *tls_warp;
+    w.x[tls_lane] = v;
+    w.bar.arrive_and_wait();
+    const float r = w.x[tls_lane ^ m];
+    w.bar.arrive_and_wait();
+    return r;
+}
 
 }  // namespace dec
 }  // namespace ggq

@@ -1,6 +1,6 @@
 // emu_decode.cpp — runs the decode family's lane-level code (csrc/decode_tile.cuh) on the CPU under a
 // 32-thread warp emulator and checks it against a scalar restatement of the block formats.
-// Usage: emu_decode <fmt 0|1|2> <T 1..16> <K> <seed>      exit 0 = pass.   Test infrastructure only.
+// Usage: emu_decode <fmt 0|1|2> <T 1..16> <K> <seed> [gemv 0|1]      exit 0 = pass.   Test infrastructure only.
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -60,7 +60,7 @@ static double weight(int fmt, const uint8_t* row, int k) {
     return d * static_cast<int8_t>(b[192 + e / 16]) * ((lo | (hi << 4)) - 32);
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, bool GV = false>
 static int run(int T, int K, unsigned seed) {
     using G = Geo<FMT>;
     const int nb = K / G::QK, rowB = nb * G::BLK;
@@ -96,7 +96,7 @@ static int run(int T, int K, unsigned seed) {
     // per-slice activation table (and, for Q4_K, the in-place permutation) exactly as the kernel builds it
     const int tpad = 8 * NT, ngrp = K / G::GROUP;
     std::vector<float> tbl(static_cast<size_t>(ngrp) * tpad + 64, 0.f);
-    stage_activations<FMT, NT>(X.data(), static_cast<uint32_t>(xpitch), tbl.data(), K, T, 0, 1);
+    stage_activations<FMT, NT, GV>(X.data(), static_cast<uint32_t>(xpitch), tbl.data(), K, T, 0, 1);
     // emulate the staging of every chunk and run the warp
     alignas(16) static uint8_t stage[16 * 1024];
     alignas(16) static uint8_t scratch[16 * 8 * 64 + 64];
@@ -133,12 +133,13 @@ static int run(int T, int K, unsigned seed) {
                 s.data_off = goff & 15;
                 s.nblk = std::min(G::PREP_BLOCKS, nblk - b);
                 s.k0 = (b0 + b) * G::QK;
-                Tile<FMT, NT>::prep(L, s);
+                Tile<FMT, NT, GV>::prep(L, s);
                 syncwarp();
-                Tile<FMT, NT>::compute(L, s, accs[lane]);
+                Tile<FMT, NT, GV>::compute(L, s, accs[lane]);
                 syncwarp();
             }
         }
+        if constexpr (GV) gemv_finalize(accs[lane]);
     };
     std::vector<std::thread> th;
     for (int l = 0; l < 32; ++l) th.emplace_back(lane_fn, l);
@@ -157,7 +158,7 @@ static int run(int T, int K, unsigned seed) {
             worst = std::max(worst, std::fabs(got - ref));
         }
     const double rel = std::sqrt(num / den);
-    std::printf("fmt=%d NT=%d T=%d K=%d rel_fro=%.3e max_abs=%.3e\n", FMT, NT, T, K, rel, worst);
+    std::printf("fmt=%d NT=%d gemv=%d T=%d K=%d rel_fro=%.3e max_abs=%.3e\n", FMT, NT, int(GV), T, K, rel, worst);
     return rel < 2e-6 ? 0 : 1;
 }
 
@@ -166,6 +167,15 @@ int main(int argc, char** argv) {
     const int fmt = std::atoi(argv[1]), T = std::atoi(argv[2]), K = std::atoi(argv[3]);
     const unsigned seed = static_cast<unsigned>(std::atoi(argv[4]));
     const bool two = T > 8;
+    if (argc > 5 && std::atoi(argv[5]) == 1) {  // single-token GEMV tile code
+        if (T != 1) return 2;
+        switch (fmt) {
+            case 0: return run<0, 1, true>(T, K, seed);
+            case 1: return run<1, 1, true>(T, K, seed);
+            case 2: return run<2, 1, true>(T, K, seed);
+        }
+        return 2;
+    }
     switch (fmt) {
         case 0: return two ? run<0, 2>(T, K, seed) : run<0, 1>(T, K, seed);
         case 1: return two ? run<1, 2>(T, K, seed) : run<1, 1>(T, K, seed);

@@ -29,3 +29,10 @@ def test_lane_code_matches_scalar_formats(emu, fmt, T, K):
         K = 4096  # Q6_K rows must be whole 16-byte vectors (K % 2048 == 0) for this family
     r = subprocess.run([emu, str(fmt), str(T), str(K), "7"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("fmt,K", [(1, 256), (1, 2048), (1, 2560), (1, 4096), (0, 256), (0, 768), (0, 4096), (2, 2048), (2, 4096)])
+def test_single_token_gemv_lane_code(emu, fmt, K):
+    """The T == 1 tile code (sub-blocks spread over the MMA columns) against the scalar format restatement."""
+    r = subprocess.run([emu, str(fmt), "1", str(K), "11", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -1,0 +1,3 @@
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+timeout 200 python tools/probe_variant.py 2>&1
+echo "== no gemv"; GGQ_NO_GEMV=1 timeout 200 python tools/probe_variant.py 2>&1 | grep -E " 1 [0-9.]+ us"
