@@ -209,37 +209,103 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     };
 
     if constexpr (AT == 1) {
-        // ======== single K-slice (the plan has AT == 1 exactly then): a flat walk over (tile, chunk) ========
-        const int tstride = static_cast<int>(gridDim.x) * WT;
-        const int tile0 = static_cast<int>(blockIdx.x) * WT + tg;
-        int ptile = tile0, pci = sub;                     // producer cursor, STG items ahead of the consumer
-        bool pdone = ptile >= p.num_tiles || sub >= p.nc;
+        // ======== single K-slice (the plan has AT == 1 exactly then): flat (tile, chunk) items ==============
+        // The CTA owns the contiguous tiles [tile_lo, tile_hi); their tiles x chunks items are cut into NW equal
+        // contiguous ranges, one per warp, so every warp streams the same number of bytes whatever O and K are.
+        // A tile cut by a range boundary is finished by the warp that holds its head: the warps holding the rest
+        // (always the FIRST thing in their range) park their partial sums in `red` and raise a flag.
+        const int tile_lo = static_cast<int>(static_cast<int64_t>(blockIdx.x) * p.num_tiles / gridDim.x);
+        const int tile_hi = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * p.num_tiles / gridDim.x);
+        const int items = (tile_hi - tile_lo) * p.nc;
+        auto range_begin = [&](int k) { return static_cast<int>(static_cast<int64_t>(k) * items / NW); };
+        const int ibeg = range_begin(w), iend = range_begin(w + 1);
+        volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES);  // [NW], zeroed below
+        float* my_slot = red + static_cast<size_t>(w) * (NT * 4 * 32);
+
+        int pi = ibeg, ptile = tile_lo + ibeg / p.nc, pci = ibeg % p.nc;  // producer cursor, STG items ahead
         auto produce = [&](int stage) {
             issue_boxes(ptile * 16, pci, stage);
-            pci += KW;
-            if (pci >= p.nc) {
-                pci = sub;
-                ptile += tstride;
-                pdone = ptile >= p.num_tiles;
+            ++pi;
+            if (++pci == p.nc) {
+                pci = 0;
+                ++ptile;
             }
         };
-        for (int s = 0; s < STG && !pdone; ++s) produce(s);
-        stage_x(0, true);
+        for (int s = 0; s < STG && pi < iend; ++s) produce(s);
+        if (tid < NW) flags[tid] = 0u;
+        stage_x(0, true);  // (its barriers also publish the cleared flags)
 
-        for (int batch = 0, tile = tile0; batch < p.num_batches; ++batch, tile += tstride) {
-            Acc<NT> acc[1];
+        auto store_tile = [&](int tile, const Acc<NT>& acc) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[0].v[nt][i] = 0.f;
-            if (tile < p.num_tiles) {  // warp-uniform
-                for (int ci = sub; ci < p.nc; ci += KW) {
-                    consume(0, ci, acc[0]);
-                    if (!pdone) produce(cstage);
-                    cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+                for (int i = 0; i < 4; ++i) {
+                    if (GV && (i & 1)) continue;  // single token: column 0 only
+                    const int64_t row = static_cast<int64_t>(tile) * 16 + L.g + ((i & 2) ? 8 : 0);
+                    const int col = 8 * nt + 2 * L.t + (i & 1);
+                    if (row < p.O && col < p.T) {
+                        const __half h = __float2half_rn(acc.v[nt][i]);
+                        const int64_t at = col * p.ldc + row;
+                        p.outs.p[0][at] = h;
+                        for (int o = 1; o < p.outs.n; ++o) p.outs.p[o][at] = h;
+                    }
+                }
+        };
+
+        int tile = tile_lo + ibeg / p.nc, ci = ibeg % p.nc;
+        bool head = ci == 0;  // does this warp hold the first chunk of the tile it is working on?
+        Acc<NT> acc;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc.v[nt][i] = 0.f;
+        for (int i = ibeg; i < iend;) {
+            consume(0, ci, acc);
+            if (pi < iend) produce(cstage);
+            cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+            ++i;
+            ++ci;
+            if (ci == p.nc || i == iend) {  // my part of `tile` is done
+                if constexpr (GV) gemv_finalize(acc);
+                if (!head) {
+                    // the tile began in an earlier warp: hand my partial sums to it
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) my_slot[(nt * 4 + r) * 32 + lane] = acc.v[nt][r];
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) flags[w] = 1u;
+                } else {
+                    if (ci != p.nc) {
+                        // the rest of the tile is in the following warps (each parks it before doing anything else)
+                        const int tile_end = (tile - tile_lo + 1) * p.nc;
+                        for (int k = w + 1; k < NW; ++k) {
+                            const int bk = range_begin(k);
+                            if (bk >= tile_end) break;
+                            if (range_begin(k + 1) == bk) continue;  // empty range
+                            while (flags[k] == 0u) {
+                            }
+                            __threadfence_block();
+                            const float* slot = red + static_cast<size_t>(k) * (NT * 4 * 32);
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc.v[nt][r] += slot[(nt * 4 + r) * 32 + lane];
+                        }
+                    }
+                    store_tile(tile, acc);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc.v[nt][r] = 0.f;
+                head = true;
+                if (ci == p.nc) {
+                    ci = 0;
+                    ++tile;
                 }
             }
-            epilogue(acc, batch);
         }
     } else {
         // ======== K-sliced walk: AT live tiles per warp share each staged activation slice ========
@@ -366,12 +432,12 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
         const uint32_t xstride = static_cast<uint32_t>(elems * 2 + xpad);
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 127) & ~size_t{127}; return o; };
-        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES));
+        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES) + 4 * MAX_NW);  // mbarriers + per-warp flags
         const size_t o_x = take(static_cast<size_t>(T) * xstride);
         const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
         const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
         const size_t o_scr = take(static_cast<size_t>(NW) * SCR_BYTES);
-        const size_t o_red = take(kw > 1 ? static_cast<size_t>(NW) * pl.nt * 4 * 32 * 4 : 0);
+        const size_t o_red = take(static_cast<size_t>(NW) * pl.nt * 4 * 32 * 4);  // one partial-sum slot per warp
         (void)at;
         if (commit) {
             p.x_stride = xstride;
@@ -403,9 +469,15 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     p.stages = stages;
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
-    pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt - 1) / wt));
-    const int rounds = (p.num_tiles + pl.grid * wt - 1) / (pl.grid * wt);
-    p.num_batches = (rounds + at - 1) / at;
+    if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA owns >= 1 tile
+        p.KW = 1;
+        pl.grid = std::max(1, std::min(sms, p.num_tiles));
+        p.num_batches = 1;
+    } else {
+        pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt - 1) / wt));
+        const int rounds = (p.num_tiles + pl.grid * wt - 1) / (pl.grid * wt);
+        p.num_batches = (rounds + at - 1) / at;
+    }
     if (a.sync) p.sync.counter_target = a.sync->counter_target + static_cast<uint32_t>(pl.grid);  // base + CTAs of this launch
     if (a.ctas_out) *a.ctas_out = pl.grid;
     return true;
