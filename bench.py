@@ -364,12 +364,13 @@ def run_ours(args):
                 {"value": total_bytes / (ms_e2e_graph * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e_graph}},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "ggq::dec::decode_kernel<Q4_K,NT=1,AT=1>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "ggq::dec::decode_kernel<Q4_K,NT=1,AT=1,GV=1> (single-token GEMV tile code)", "achieved": achieved,
                      "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "us_per_launch": ms_k * 1e3,
                      "algorithmic_bytes_per_launch": k_bytes,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/, N=1 only)
-                     "traffic": 295552512 + 3876096 if world == 1 else None},
+                     "traffic": 297801984 + 6155776 if world == 1 else None,
+                     "traffic_source": "ncu --set full, profiles/r1b_decode_q4k_T1_lmhead_ncu_summary.csv (dram read + write bytes of one launch)"},
         "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_rows} of {O} rows, one pass ({cpu_dt:.1f} s), numpy oracle port of kernels/cpu_impls"},
         "parity": parity,

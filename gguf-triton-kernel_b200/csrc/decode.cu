@@ -137,7 +137,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 
     const bool skip_math = p.dbg_skip_compute != 0;
     const int tok0 = min(L.g, p.T - 1), tok1 = min(8 + L.g, p.T - 1);
-    uint32_t full_phase = 0, x_phase = 0;
+    uint32_t ring_phase = 0, x_phase = 0;
     int cstage = 0;
 
     // ---- stage one K-slice of the activations + its block-sum table (all threads) -------------------
@@ -164,20 +164,33 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     };
 
     // ---- consume the chunk sitting in ring stage `cstage` (chunk `ci` of K-slice `slice`) -----------
+    // ring stages are used round-robin, so all stages of one lap share the mbarrier parity `ring_phase`
+    StageArgs sa;
+    sa.xrow[0] = xs + tok0 * p.x_stride;
+    sa.xrow[1] = xs + tok1 * p.x_stride;
+    sa.xv[0] = L.g < p.T;
+    sa.xv[1] = 8 + L.g < p.T;
+    sa.tbl = tbl;
+    sa.scratch = scr;
     auto consume = [&](int slice, int ci, Acc<NT>& acc) {
-        mbar_wait(my_full + cstage, (full_phase >> cstage) & 1u);
-        full_phase ^= 1u << cstage;
+        mbar_wait(my_full + cstage, ring_phase);
+        if (skip_math) return;
         const int b0 = (slice * p.cps + ci) * G::CHUNK_BLOCKS;
-        const int nblk = min(G::CHUNK_BLOCKS, p.nb - b0);
-        StageArgs s;
-        s.xrow[0] = xs + tok0 * p.x_stride;
-        s.xrow[1] = xs + tok1 * p.x_stride;
-        s.xv[0] = L.g < p.T;
-        s.xv[1] = 8 + L.g < p.T;
-        s.tbl = tbl;
-        s.scratch = scr;
+        StageArgs s = sa;
         s.data_off = (b0 * G::BLK) & 15;
-        if (!skip_math) {
+        if (b0 + G::CHUNK_BLOCKS <= p.nb) {  // whole chunk (warp-uniform): no bounds checks anywhere below
+#pragma unroll
+            for (int u = 0; u < SUBTILES; ++u) {
+                s.rows = ring + cstage * STAGE_BYTES + u * 16 * G::SLOT;
+                s.nblk = G::PREP_BLOCKS;
+                s.k0 = ci * G::CHUNK_ELEMS + u * G::PREP_BLOCKS * G::QK;
+                Tile<FMT, NT, GV>::template prep<true>(L, s);
+                __syncwarp();
+                Tile<FMT, NT, GV>::template compute<true>(L, s, acc);
+                __syncwarp();  // all lanes are done reading the stage and the scratch
+            }
+        } else {
+            const int nblk = p.nb - b0;
 #pragma unroll
             for (int u = 0; u < SUBTILES; ++u) {
                 const int b = u * G::PREP_BLOCKS;
@@ -185,12 +198,18 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     s.rows = ring + cstage * STAGE_BYTES + u * 16 * G::SLOT;
                     s.nblk = min(G::PREP_BLOCKS, nblk - b);
                     s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
-                    Tile<FMT, NT, GV>::prep(L, s);
+                    Tile<FMT, NT, GV>::template prep<false>(L, s);
                     __syncwarp();
-                    Tile<FMT, NT, GV>::compute(L, s, acc);
-                    __syncwarp();  // all lanes are done reading the stage and the scratch
+                    Tile<FMT, NT, GV>::template compute<false>(L, s, acc);
+                    __syncwarp();
                 }
             }
+        }
+    };
+    auto next_stage = [&]() {
+        if (++cstage == STG) {
+            cstage = 0;
+            ring_phase ^= 1u;
         }
     };
     // one elected lane: the 2-D TMA boxes (16 rows x SLOT bytes of the raw packed rows, each starting at the 16-byte
@@ -262,7 +281,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         for (int i = ibeg; i < iend;) {
             consume(0, ci, acc);
             if (pi < iend) produce(cstage);
-            cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+            next_stage();
             ++i;
             ++ci;
             if (ci == p.nc || i == iend) {  // my part of `tile` is done
@@ -353,7 +372,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     for (int ci = sub; ci < nsc; ci += KW) {
                         consume(slice, ci, acc[a]);
                         if (!pc.done) produce(cstage);
-                        cstage = (cstage + 1 == STG) ? 0 : cstage + 1;
+                        next_stage();
                     }
                 }
             }

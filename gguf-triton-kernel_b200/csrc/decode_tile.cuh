@@ -152,7 +152,7 @@ GGQ_DEV void q8_to_h2(uint32_t w, uint32_t& lo, uint32_t& hi) {
     hi = prmt(u, 0u, 0x7362);
 }
 
-template <int NT>
+template <int NT, bool FULL>
 GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     using G = Geo<0>;
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
@@ -161,7 +161,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const int t4 = 4 * L.t;
 #pragma unroll
     for (int p = 0; p < G::PREP_BLOCKS / 2; ++p) {
-        if (2 * p >= s.nblk) break;
+        if (!FULL && 2 * p >= s.nblk) break;
         const uint8_t* a = r0 + 68 * p;
         const uint8_t* b = r1 + 68 * p;
         const uint32_t a0w = ld32(a), a8w = ld32(a + 32), b0w = ld32(b), b8w = ld32(b + 32);
@@ -225,6 +225,7 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // Lane (g, t) loads the activations of block g of the 8-block group in the pattern of that block's parity (even
 // blocks: k = 2 + 4t.., odd blocks: k = 4t..) once per group; column j of block j's MMAs is the dot product, held by
 // lane t == j / 2, which also is the only lane that converts that block's scale.
+template <bool FULL>
 GGQ_DEV void compute_q8_0_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
     using G = Geo<0>;
     const uint8_t* r0 = s.rows + L.g * G::SLOT + s.data_off;
@@ -236,7 +237,7 @@ GGQ_DEV void compute_q8_0_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
     float a0 = acc.v[0][0], a1 = acc.v[0][1], a2 = acc.v[0][2], a3 = acc.v[0][3];
 #pragma unroll
     for (int u = 0; u < G::PREP_BLOCKS / 8; ++u) {
-        if (8 * u >= s.nblk) break;
+        if (!FULL && 8 * u >= s.nblk) break;
         const int kb8 = s.k0 + 256 * u;
         const uint8_t* x = s.xrow[0] + 2 * (kb8 + 32 * L.g);
         const uint32_t b1[2] = {ld32(x + 2 * o1), ld32(x + 2 * (o1 + 2))};
@@ -305,9 +306,10 @@ GGQ_DEV uint32_t bf16_bits_rn(float f) {  // float -> bf16 bit pattern, round to
     return u >> 16;
 }
 
+template <bool FULL>
 GGQ_DEV void prep_q4_k(const Lane& L, const StageArgs& s) {
     using G = Geo<1>;
-    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+    for (int p = L.lane; p < 16 * (FULL ? G::PREP_BLOCKS : s.nblk); p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
         const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
@@ -476,11 +478,6 @@ GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) 
     }
 }
 
-template <int NT>
-GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
-    if (s.nblk == Geo<1>::PREP_BLOCKS) compute_q4_k_impl<NT, true>(L, s, acc);
-    else compute_q4_k_impl<NT, false>(L, s, acc);
-}
 
 
 // ---- Q4_K, one token (GEMV) ----------------------------------------------------------------------
@@ -495,9 +492,10 @@ GGQ_DEV void compute_q4_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // prep: scratch entry = 64 B per (row, block): four 16-byte pieces {s_2t, s_2t+1, -dmin*m_2t, -dmin*m_2t+1},
 // piece t stored at position t ^ ((row >> 1) & 3) so that both the 128-bit stores of prep (lane = row) and the
 // 128-bit loads of compute (lane = (g, t)) are bank-conflict free.
+template <bool FULL>
 GGQ_DEV void prep_q4_k_gv(const Lane& L, const StageArgs& s) {
     using G = Geo<1>;
-    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+    for (int p = L.lane; p < 16 * (FULL ? G::PREP_BLOCKS : s.nblk); p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint4 h = ld128(s.rows + row * G::SLOT + s.data_off + blk * G::BLK);
         const float d = h2f(h.x & 0xffffu), dmin = h2f(h.x >> 16);
@@ -617,10 +615,6 @@ GGQ_DEV void compute_q4_k_gv_impl(const Lane& L, const StageArgs& s, Acc<1>& acc
     acc.v[0][3] = a3;
 }
 
-GGQ_DEV void compute_q4_k_gv(const Lane& L, const StageArgs& s, Acc<1>& acc) {
-    if (s.nblk == Geo<1>::PREP_BLOCKS) compute_q4_k_gv_impl<true>(L, s, acc);
-    else compute_q4_k_gv_impl<false>(L, s, acc);
-}
 
 // GEMV accumulators -> the standard C-fragment layout (column 0 = the token): v[0] = row g, v[2] = row g + 8
 GGQ_DEV void gemv_finalize(Acc<1>& acc) {
@@ -639,9 +633,10 @@ GGQ_DEV void gemv_finalize(Acc<1>& acc) {
 // Q6_K
 // =============================================================================================
 // prep: scratch[blk * 16 + row][(h*2 + lh)*4 + grp] = d * sc[8h + 2grp + lh] * 2^24  (fp32, exact)
+template <bool FULL>
 GGQ_DEV void prep_q6_k(const Lane& L, const StageArgs& s) {
     using G = Geo<2>;
-    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+    for (int p = L.lane; p < 16 * (FULL ? G::PREP_BLOCKS : s.nblk); p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
         const float d = h2f(ld16(b + 208)) * 16777216.f;
@@ -744,9 +739,10 @@ GGQ_DEV void compute_q6_k(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
 // ---- Q6_K, one token (GEMV): the 8 MMA columns carry the 8 sub-blocks (16 weights each) of half a block ----------
 // prep: scratch entry = 64 B per (row, block); piece t = d * 2^24 * {sc[2t], sc[2t+1], sc[8+2t], sc[8+2t+1]} (the four
 // sub-blocks whose column lives in lane t), stored at position t ^ ((row >> 1) & 3) (conflict-free stores and loads).
+template <bool FULL>
 GGQ_DEV void prep_q6_k_gv(const Lane& L, const StageArgs& s) {
     using G = Geo<2>;
-    for (int p = L.lane; p < 16 * s.nblk; p += 32) {
+    for (int p = L.lane; p < 16 * (FULL ? G::PREP_BLOCKS : s.nblk); p += 32) {
         const int row = p & 15, blk = p >> 4;
         const uint8_t* b = s.rows + row * G::SLOT + s.data_off + blk * G::BLK;  // 2-byte aligned
         const float d = h2f(ld16(b + 208)) * 16777216.f;
@@ -902,30 +898,31 @@ GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int n
 }
 
 // ---- format dispatch ---------------------------------------------------------------------------
+// FULL = the sub-step holds all PREP_BLOCKS blocks (the common case: no bounds checks, prep is a single pass)
 template <int FMT, int NT, bool GV = false> struct Tile;
 template <> struct Tile<0, 1, true> {
-    static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q8_0_gv(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q8_0_gv<FULL>(L, s, a); }
 };
 template <> struct Tile<2, 1, true> {
-    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k_gv(L, s); }
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q6_k_gv(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k_gv<FULL>(L, s); }
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q6_k_gv(L, s, a); }
 };
 template <> struct Tile<1, 1, true> {
-    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k_gv(L, s); }
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q4_k_gv(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k_gv<FULL>(L, s); }
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<1>& a) { compute_q4_k_gv_impl<FULL>(L, s, a); }
 };
 template <int NT> struct Tile<0, NT, false> {
-    static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q8_0<NT>(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane&, const StageArgs&) {}
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q8_0<NT, FULL>(L, s, a); }
 };
 template <int NT> struct Tile<1, NT, false> {
-    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k(L, s); }
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q4_k<NT>(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q4_k<FULL>(L, s); }
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q4_k_impl<NT, FULL>(L, s, a); }
 };
 template <int NT> struct Tile<2, NT, false> {
-    static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k(L, s); }
-    static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q6_k<NT>(L, s, a); }
+    template <bool FULL> static GGQ_DEV void prep(const Lane& L, const StageArgs& s) { prep_q6_k<FULL>(L, s); }
+    template <bool FULL> static GGQ_DEV void compute(const Lane& L, const StageArgs& s, Acc<NT>& a) { compute_q6_k<NT>(L, s, a); }
 };
 
 }  // namespace dec

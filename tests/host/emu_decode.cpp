@@ -133,9 +133,15 @@ static int run(int T, int K, unsigned seed) {
                 s.data_off = goff & 15;
                 s.nblk = std::min(G::PREP_BLOCKS, nblk - b);
                 s.k0 = (b0 + b) * G::QK;
-                Tile<FMT, NT, GV>::prep(L, s);
-                syncwarp();
-                Tile<FMT, NT, GV>::compute(L, s, accs[lane]);
+                if (s.nblk == G::PREP_BLOCKS) {  // the kernel's fast path
+                    Tile<FMT, NT, GV>::template prep<true>(L, s);
+                    syncwarp();
+                    Tile<FMT, NT, GV>::template compute<true>(L, s, accs[lane]);
+                } else {
+                    Tile<FMT, NT, GV>::template prep<false>(L, s);
+                    syncwarp();
+                    Tile<FMT, NT, GV>::template compute<false>(L, s, accs[lane]);
+                }
                 syncwarp();
             }
         }
