@@ -142,6 +142,7 @@ int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const*
     for (int i = 0; i < 8; ++i) ps.flags_peer[i] = sync->flags_peer[i];
     ps.counter = sync->counter;
     ps.x_ready = sync->x_ready;
+    ps.x_publish = sync->x_publish;
     ps.epoch = sync->epoch;
     ps.counter_target = sync->counter_base;  // the planner adds the grid size
     ps.rank = sync->rank;

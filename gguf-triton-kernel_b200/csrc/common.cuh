@@ -12,6 +12,7 @@ struct PeerSync {
     uint32_t* flags_peer[8];
     uint32_t* counter;
     const uint32_t* x_ready;
+    uint32_t* x_publish;
     uint32_t epoch, counter_target;
     int rank, world;
 };

@@ -80,6 +80,11 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     uint64_t* my_full = bars + 1 + w * STG;
 
     if (tid == 0) {
+        if (p.sync.x_publish != nullptr && blockIdx.x == 0) {
+            // this rank owns the activations (written earlier in stream order): tell the peers they may read them
+            __threadfence_system();
+            st_release_sys(p.sync.x_publish, p.sync.epoch);
+        }
         prefetch_tmap(&map_w);
         mbar_init(&bars[0], 1);
         for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);

@@ -138,7 +138,7 @@ class NSplitLinear:
         self._ctas = ctypes.c_int(0)
         self._ctas_ref = ctypes.byref(self._ctas)
         self._a_ptr = self.A.data_ptr()
-        self._flag_x = self._flags[8:9]   # rank 0's "activations of epoch e are in place" word
+        self._flag_x_ptr = self._flags.data_ptr() + 8 * 4   # rank 0's "activations of epoch e are in place" word
 
     def input_buffer(self, T: int) -> torch.Tensor:
         """Rank 0: the symmetric [T, K] buffer the NEXT fused decode step reads its activations from.  Writing the
@@ -154,11 +154,12 @@ class NSplitLinear:
         cur = self._epoch & 1
         sync = self._sync
         sync.x_ready = 0
+        sync.x_publish = 0
         if broadcast and self.world > 1:
             if self.rank == 0:
                 if X is not None and X.data_ptr() != self._x_local[cur]:
-                    self._xbuf[cur, :T].copy_(X)          # stream-ordered: lands before the ready word
-                self._flag_x.fill_(self._epoch)             # stream-ordered after the activations landed
+                    self._xbuf[cur, :T].copy_(X)          # stream-ordered: lands before the kernel below starts
+                sync.x_publish = self._flag_x_ptr           # the kernel raises the ready word itself
                 x_ptr = self._x_local[cur]
             else:
                 x_ptr = self._x_rank0[cur]                # rank 0's buffer over NVLink

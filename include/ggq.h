@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 100 /* 0.1.0 */
+#define GGQ_VERSION 101 /* 0.1.1 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -82,7 +82,8 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
 /*
  * Decode-family GEMV/skinny GEMM with the N-split exchange fused INTO the kernel (T <= 16):
  *   - activations may live in another rank's memory (X = NVLink peer pointer to rank 0's buffer); if
- *     `x_ready` is non-NULL every CTA first waits until *x_ready >= epoch (acquire, system scope);
+ *     `x_ready` is non-NULL every CTA first waits until *x_ready >= epoch (acquire, system scope); the owning
+ *     rank's kernel raises that word itself when `x_publish` is set;
  *   - every output tile is stored to all C_out[i] (own + peer [T, ldc] buffers);
  *   - at the end the last CTA publishes `epoch` into flags_peer[p][rank] of every peer (release, system
  *     scope) and waits until every peer has published its own into flags_local[p]: when the kernel
@@ -100,6 +101,9 @@ typedef struct ggq_peer_sync {
     uint32_t epoch;
     uint32_t counter_base;
     int32_t rank, world;
+    uint32_t* x_publish; /* rank that OWNS the activations: its "ready" word (the one the peers pass as x_ready); the
+                            kernel stores `epoch` there when it starts (the activations were written earlier in
+                            stream order), so no separate flag kernel is needed.  NULL on the other ranks. */
 } ggq_peer_sync;
 
 /* Returns 0 and writes the number of CTAs launched to *ctas_out (the caller advances counter_base by it). */
