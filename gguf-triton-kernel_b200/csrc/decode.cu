@@ -79,6 +79,9 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     float* red = reinterpret_cast<float*>(smem + p.off_red);
     uint64_t* my_full = bars + 1 + w * STG;
 
+    // Programmatic dependent launch: the next kernel in the stream may start its own prologue (barrier init, weight
+    // prefetch) while this one runs; everything that depends on earlier kernels sits behind pdl_wait() in stage_x.
+    pdl_launch_dependents();
     if (tid == 0) {
         if (p.sync.x_publish != nullptr && blockIdx.x == 0) {
             // this rank owns the activations (written earlier in stream order): tell the peers they may read them
@@ -151,6 +154,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
         __syncthreads();  // every warp is done with the previous slice's x / tbl
         if (tid == 0) {
+            if (first) pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
             if (p.sync.world > 0 && p.sync.x_ready != nullptr && first) {
                 // activations are produced by rank 0 (peer memory): wait for its "ready" word of this step
                 while (ld_acquire_sys(p.sync.x_ready) < p.sync.epoch) {
@@ -540,9 +544,20 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
                      static_cast<uint64_t>(pl.p.O), static_cast<uint64_t>(pl.p.rowB), Geo<FMT>::SLOT / 4, 16,
                      CU_TENSOR_MAP_SWIZZLE_NONE))
         return static_cast<int>(cudaErrorInvalidValue);
-    kern<<<pl.grid, NW * 32, pl.smem, stream>>>(map_w, pl.p);
+    static const bool no_pdl = getenv("GGQ_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (no_pdl || pl.p.sync.world > 1) ? 0 : 1;  // not with the in-kernel cross-GPU exchange (spin waits)
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, map_w, pl.p);
     count_launch();
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 template <int FMT>

@@ -36,6 +36,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- programmatic dependent launch (sm_90+): no-ops when the kernel was launched without the attribute ----
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (UBLKCP) --------------------
 // dst, src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

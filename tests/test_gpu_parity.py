@@ -312,3 +312,54 @@ def test_prefill_matches_decode_on_the_same_problem(ext, fmt):
     Cp = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_PREFILL).astype(np.float32)
     mx, fro = orc.tier1_errors(Cd, Cp)
     assert fro < 1e-3 and mx < 5e-3, (mx, fro)
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_decode_chain_of_dependent_launches(ext, fmt):
+    """Decode launches overlap their prologue with the previous kernel (programmatic dependent launch).  A chain in
+    which every launch consumes the previous launch's output — back to back on one stream, and replayed from a CUDA
+    graph — must give exactly what the same chain gives with a device synchronisation after every launch."""
+    K = 2048
+    f = ext.FMT_ID[fmt]
+    Ws = [dev(orc.random_blocks(fmt, K, K, seed=70 + i)) for i in range(4)]
+    x0 = (torch.randn((3, K), device="cuda:0", dtype=torch.float32) * 0.1).half()
+
+    def chain(sync):
+        x = x0
+        outs = []
+        for i in range(12):
+            y = torch.empty((3, K), device="cuda:0", dtype=torch.float16)
+            ext.mm(f, Ws[i % 4], x, K, 3, K, family=ext.FAMILY_DECODE, out=y)
+            if sync:
+                torch.cuda.synchronize()
+            # even hops feed the next launch directly; odd hops go through foreign (torch) kernels that also keep the
+            # magnitudes in fp16 range (one hop multiplies them by 30-100)
+            x = y if i % 2 == 0 else (y * 2e-5).clamp_(-0.1, 0.1)
+            outs.append(y)
+        torch.cuda.synchronize()
+        return torch.stack(outs)
+
+    ref = chain(True)
+    got = chain(False)
+    assert torch.isfinite(ref.float()).all() and ref.float().abs().max() > 0
+    assert torch.equal(ref, got)
+    # two-hop chains from a CUDA graph, replayed
+    u = [torch.empty((3, K), device="cuda:0", dtype=torch.float16) for _ in range(6)]
+    v = [torch.empty((3, K), device="cuda:0", dtype=torch.float16) for _ in range(6)]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(6):
+            ext.mm(f, Ws[i % 4], x0, K, 3, K, family=ext.FAMILY_DECODE, out=u[i])
+            ext.mm(f, Ws[(i + 1) % 4], u[i], K, 3, K, family=ext.FAMILY_DECODE, out=v[i])
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for i in range(6):
+        a = torch.empty_like(u[i])
+        b = torch.empty_like(v[i])
+        ext.mm(f, Ws[i % 4], x0, K, 3, K, family=ext.FAMILY_DECODE, out=a)
+        torch.cuda.synchronize()
+        ext.mm(f, Ws[(i + 1) % 4], a, K, 3, K, family=ext.FAMILY_DECODE, out=b)
+        torch.cuda.synchronize()
+        assert torch.equal(a, u[i]) and torch.equal(b, v[i]), i
