@@ -53,7 +53,7 @@ struct Params {
     int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
     PeerSync sync;      // world == 0: no cross-GPU synchronisation
     uint32_t x_stride;  // bytes between token rows in shared memory
-    uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red;
+    uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red, off_mbox;
 };
 
 // NW warps per CTA, MINB CTAs per SM (register budget), NT 8-token n-tiles, AT live tiles per warp
@@ -77,6 +77,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     uint8_t* ring = smem + p.off_ring + static_cast<size_t>(w) * STG * STAGE_BYTES;
     uint8_t* scr = smem + p.off_scr + static_cast<size_t>(w) * SCR_BYTES;
     float* red = reinterpret_cast<float*>(smem + p.off_red);
+    float* mbox = reinterpret_cast<float*>(smem + p.off_mbox);
     uint64_t* my_full = bars + 1 + w * STG;
 
     // Programmatic dependent launch: the next kernel in the stream may start its own prologue (barrier init, weight
@@ -91,6 +92,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         prefetch_tmap(&map_w);
         mbar_init(&bars[0], 1);
         for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);
+        for (int i = 0; i < 2 * MAX_NW; ++i) mbar_init(&bars[1 + MAX_NW * MAX_STAGES + i], 1);  // cluster mailboxes
         fence_mbar_init();
     }
     __syncthreads();
@@ -242,26 +244,46 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         // contiguous ranges, one per warp, so every warp streams the same number of bytes whatever O and K are.
         // A tile cut by a range boundary is finished by the warp that holds its head: the warps holding the rest
         // (always the FIRST thing in their range) park their partial sums in `red` and raise a flag.
-        const int tile_lo = static_cast<int>(static_cast<int64_t>(blockIdx.x) * p.num_tiles / gridDim.x);
-        const int tile_hi = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * p.num_tiles / gridDim.x);
-        const int items = (tile_hi - tile_lo) * p.nc;
+        // Cluster split-K (S = p.n_slices > 1, launched as clusters of S CTAs): when the activations of all tokens do
+        // not fit in one CTA's shared memory, CTA r of a cluster stages only K-slice r of them and walks the SAME
+        // (tile, chunk) items over its slice of every row.  The partial sums of a warp's part of a tile travel down
+        // the cluster, rank S-1 -> ... -> rank 0, through one distributed-shared-memory mailbox per warp (the warps
+        // with the same index run the same item sequence in every rank); rank 0 then finishes the tile as usual.
+        const int S = p.n_slices;
+        const int crank = S > 1 ? static_cast<int>(cl_ctarank()) : 0;
+        const int ncl = static_cast<int>(gridDim.x) / S, cl = static_cast<int>(blockIdx.x) / S;
+        const int tile_lo = static_cast<int>(static_cast<int64_t>(cl) * p.num_tiles / ncl);
+        const int tile_hi = static_cast<int>(static_cast<int64_t>(cl + 1) * p.num_tiles / ncl);
+        const int nsc = p.cps;                                    // logical chunks per tile, the same in every rank
+        const int nsc_mine = min(p.cps, p.nc - crank * p.cps);    // chunks that exist in my slice (the last may be short)
+        const int items = (tile_hi - tile_lo) * nsc;
         auto range_begin = [&](int k) { return static_cast<int>(static_cast<int64_t>(k) * items / NW); };
         const int ibeg = range_begin(w), iend = range_begin(w + 1);
-        volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES);  // [NW], zeroed below
+        uint64_t* mb_full = bars + 1 + MAX_NW * MAX_STAGES + w;            // my mailbox has been filled (by rank + 1)
+        uint64_t* mb_empty = bars + 1 + MAX_NW * MAX_STAGES + MAX_NW + w;  // rank - 1 has read my last message
+        volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES + 2 * MAX_NW);  // [NW] intra-CTA hand-off
         float* my_slot = red + static_cast<size_t>(w) * (NT * 4 * 32);
+        float4* my_mbox = reinterpret_cast<float4*>(mbox) + static_cast<size_t>(w) * (NT * 32);
+        uint32_t sent = 0, full_phase = 0, empty_phase = 0;
 
-        int pi = ibeg, ptile = tile_lo + ibeg / p.nc, pci = ibeg % p.nc;  // producer cursor, STG items ahead
-        auto produce = [&](int stage) {
-            issue_boxes(ptile * 16, pci, stage);
+        int pi = ibeg, ptile = tile_lo + ibeg / nsc, pci = ibeg % nsc;  // producer cursor, STG real items ahead
+        auto p_advance = [&]() {
             ++pi;
-            if (++pci == p.nc) {
+            if (++pci == nsc) {
                 pci = 0;
                 ++ptile;
             }
         };
+        auto produce = [&](int stage) {
+            issue_boxes(ptile * 16, crank * p.cps + pci, stage);
+            p_advance();
+            while (pi < iend && pci >= nsc_mine) p_advance();  // chunks past the end of a short last slice do not exist
+        };
+        while (pi < iend && pci >= nsc_mine) p_advance();
         for (int s = 0; s < STG && pi < iend; ++s) produce(s);
         if (tid < NW) flags[tid] = 0u;
-        stage_x(0, true);  // (its barriers also publish the cleared flags)
+        if (S > 1) cl_sync();     // every CTA of the cluster runs and has initialised its barriers before anyone signals them
+        stage_x(crank, true);     // (its barriers also publish the cleared flags inside the CTA)
 
         auto store_tile = [&](int tile, const Acc<NT>& acc) {
 #pragma unroll
@@ -280,7 +302,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 }
         };
 
-        int tile = tile_lo + ibeg / p.nc, ci = ibeg % p.nc;
+        int tile = tile_lo + ibeg / nsc, ci = ibeg % nsc;
         bool head = ci == 0;  // does this warp hold the first chunk of the tile it is working on?
         Acc<NT> acc;
 #pragma unroll
@@ -288,14 +310,48 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc.v[nt][i] = 0.f;
         for (int i = ibeg; i < iend;) {
-            consume(0, ci, acc);
-            if (pi < iend) produce(cstage);
-            next_stage();
+            if (ci < nsc_mine) {
+                consume(crank, ci, acc);
+                if (pi < iend) produce(cstage);
+                next_stage();
+            }
             ++i;
             ++ci;
-            if (ci == p.nc || i == iend) {  // my part of `tile` is done
+            if (ci == nsc || i == iend) {  // my part of `tile` is done
                 if constexpr (GV) gemv_finalize(acc);
-                if (!head) {
+                bool mine = true;          // does this CTA finish / hand over the part inside the CTA?
+                if (S > 1) {
+                    if (crank < S - 1) {   // add what the ranks above me accumulated for this part
+                        if (lane == 0) mbar_arrive_expect_tx(mb_full, NT * 4 * 32 * 4);
+                        mbar_wait(mb_full, full_phase);
+                        full_phase ^= 1u;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            const float4 v = my_mbox[nt * 32 + lane];
+                            acc.v[nt][0] += v.x;
+                            acc.v[nt][1] += v.y;
+                            acc.v[nt][2] += v.z;
+                            acc.v[nt][3] += v.w;
+                        }
+                        __syncwarp();
+                        if (lane == 0) cl_mbar_arrive(cl_map(smem_u32(mb_empty), crank + 1));
+                    }
+                    if (crank > 0) {       // pass it down
+                        if (sent > 0) {    // the previous message has been read
+                            cl_mbar_wait(mb_empty, empty_phase);
+                            empty_phase ^= 1u;
+                        }
+                        const uint32_t dst = cl_map(smem_u32(my_mbox), crank - 1);
+                        const uint32_t dbar = cl_map(smem_u32(mb_full), crank - 1);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            cl_st_async_f32x4(dst + (nt * 32 + lane) * 16, acc.v[nt][0], acc.v[nt][1], acc.v[nt][2], acc.v[nt][3], dbar);
+                        ++sent;
+                        mine = false;
+                    }
+                }
+                if (!mine) {
+                } else if (!head) {
                     // the tile began in an earlier warp: hand my partial sums to it
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
@@ -305,9 +361,9 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     __syncwarp();
                     if (lane == 0) flags[w] = 1u;
                 } else {
-                    if (ci != p.nc) {
+                    if (ci != nsc) {
                         // the rest of the tile is in the following warps (each parks it before doing anything else)
-                        const int tile_end = (tile - tile_lo + 1) * p.nc;
+                        const int tile_end = (tile - tile_lo + 1) * nsc;
                         for (int k = w + 1; k < NW; ++k) {
                             const int bk = range_begin(k);
                             if (bk >= tile_end) break;
@@ -329,12 +385,13 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc.v[nt][r] = 0.f;
                 head = true;
-                if (ci == p.nc) {
+                if (ci == nsc) {
                     ci = 0;
                     ++tile;
                 }
             }
         }
+        if (S > 1) cl_sync();  // nobody writes into the shared memory of a CTA that has exited
     } else {
         // ======== K-sliced walk: AT live tiles per warp share each staged activation slice ========
         auto tile_of = [&](int batch, int a) -> int64_t {
@@ -417,7 +474,7 @@ struct Plan {
 
 // One configuration attempt: NW warps per CTA, OCC CTAs per SM.
 template <int FMT>
-static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_slicing, Plan& pl) {
+static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_slicing, Plan& pl, int S = 1) {
     using G = Geo<FMT>;
     Params& p = pl.p;
     p = Params{};
@@ -460,12 +517,13 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
         const uint32_t xstride = static_cast<uint32_t>(elems * 2 + xpad);
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 127) & ~size_t{127}; return o; };
-        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES) + 4 * MAX_NW);  // mbarriers + per-warp flags
+        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + 4 * MAX_NW);  // mbarriers + a flag word per warp
         const size_t o_x = take(static_cast<size_t>(T) * xstride);
         const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
         const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
         const size_t o_scr = take(static_cast<size_t>(NW) * SCR_BYTES);
         const size_t o_red = take(static_cast<size_t>(NW) * pl.nt * 4 * 32 * 4);  // one partial-sum slot per warp
+        const size_t o_mbox = take(S > 1 ? static_cast<size_t>(NW) * pl.nt * 4 * 32 * 4 : 0);  // cluster mailboxes
         (void)at;
         if (commit) {
             p.x_stride = xstride;
@@ -475,13 +533,18 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
             p.off_ring = static_cast<uint32_t>(o_ring);
             p.off_scr = static_cast<uint32_t>(o_scr);
             p.off_red = static_cast<uint32_t>(o_red);
+            p.off_mbox = static_cast<uint32_t>(o_mbox);
         }
         return off;
     };
 
     // whole K in one slice if it fits next to a >= 2-stage ring; otherwise the largest even slicing
     int cps = p.nc, at = 1, stages = 2;
-    if (layout(cps, 2, 1, false) > static_cast<size_t>(SMEM_LIMIT)) {
+    if (S > 1) {  // cluster split-K: CTA r of a cluster of S owns K-slice r (cps chunks; the last slice may be shorter)
+        cps = (p.nc + S - 1) / S;
+        if (cps * (S - 1) >= p.nc || OCC != 1 || a.sync) return false;
+        if (layout(cps, 2, 1, false) > static_cast<size_t>(SMEM_LIMIT)) return false;
+    } else if (layout(cps, 2, 1, false) > static_cast<size_t>(SMEM_LIMIT)) {
         if (!allow_slicing) return false;
         at = 4;
         int slices = 2;
@@ -497,9 +560,9 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     p.stages = stages;
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
-    if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA owns >= 1 tile
+    if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA / cluster owns >= 1 tile
         p.KW = 1;
-        pl.grid = std::max(1, std::min(sms, p.num_tiles));
+        pl.grid = S * std::max(1, std::min(sms / S, p.num_tiles));
         p.num_batches = 1;
     } else {
         pl.grid = std::max(1, std::min(sms, (p.num_tiles + wt - 1) / wt));
@@ -518,11 +581,32 @@ template <int FMT>
 static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     if (const char* f = getenv("GGQ_PLAN_FORCE")) {  // dev: "8,2" | "12,1" | "8,1"
         const int nw = atoi(f), occ = (strchr(f, ',') ? atoi(strchr(f, ',') + 1) : 1);
-        return make_plan_cfg<FMT>(a, T, nw, occ, nw == 8 && occ == 1, pl);
+        const char* c2 = strchr(f, ',') ? strchr(strchr(f, ',') + 1, ',') : nullptr;
+        const int S = c2 ? atoi(c2 + 1) : 1;
+        return make_plan_cfg<FMT>(a, T, nw, occ, nw == 8 && occ == 1 && S == 1, pl, S);
     }
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 3) return true;
     if (make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 2) return true;
+    if (make_plan_cfg<FMT>(a, T, 8, 1, false, pl) && pl.p.stages >= 2) return true;
+    // the activations of all tokens do not fit in one CTA: clusters of 2 / 4 / 8 CTAs split K (and the activations)
+    if (!getenv("GGQ_NO_CLUSTER")) {
+        // smallest padding of K first (S * cps chunks are walked for nc real ones), then the smaller cluster (fewer
+        // hops, and small clusters tile the GPCs without leaving SMs idle), then 12 warps before 8
+        int best_s = 0, best_nw = 0, best_waste = 1 << 30;
+        for (int S = 2; S <= 8; ++S)
+            for (int nw = 12; nw >= 8; nw -= 4) {
+                Plan t;
+                if (!make_plan_cfg<FMT>(a, T, nw, 1, false, t, S) || t.p.stages < 2) continue;
+                const int waste = S * t.p.cps * 1024 / t.p.nc;
+                if (waste < best_waste) {
+                    best_waste = waste;
+                    best_s = S;
+                    best_nw = nw;
+                }
+            }
+        if (best_s) return make_plan_cfg<FMT>(a, T, best_nw, 1, false, pl, best_s);
+    }
     return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
 }
 
@@ -550,11 +634,31 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
     cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    const int S = (AT == 1) ? pl.p.n_slices : 1;
+    if (S > 1) {  // cluster split-K: as many clusters as can be co-resident (the kernel is persistent)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = S;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+            cudaGetLastError();
+            return GGQ_E_FAMILY;
+        }
+        cfg.gridDim = dim3(S * std::max(1, std::min(max_clusters, pl.grid / S)));
+    }
+    if (!(no_pdl || pl.p.sync.world > 1)) {  // not with the in-kernel cross-GPU exchange (spin waits)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (no_pdl || pl.p.sync.world > 1) ? 0 : 1;  // not with the in-kernel cross-GPU exchange (spin waits)
+    cfg.numAttrs = na;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, map_w, pl.p);
     count_launch();
     return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());

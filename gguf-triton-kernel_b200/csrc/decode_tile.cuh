@@ -120,12 +120,30 @@ GGQ_DEV uint4 ld128p(const uint8_t* p, bool v) { return v ? *reinterpret_cast<co
 // Predicated shared-memory load that KEEPS the destination of inactive lanes (no zeroing): the lanes whose token does
 // not exist feed MMA columns that are never stored, so whatever they hold is fine.
 GGQ_DEV void ld128k(uint4& d, const uint8_t* p, bool v) {
-#if defined(__CUDACC__) && defined(GGQ_XLOAD_ASM)
+#ifdef __CUDACC__
     asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n @q ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n}\n"
                  : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w)
                  : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(static_cast<int>(v)));
 #else
     if (v) d = *reinterpret_cast<const uint4*>(p);
+#endif
+}
+GGQ_DEV void ld64k(uint2& d, const uint8_t* p, bool v) {
+#ifdef __CUDACC__
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n @q ld.shared.v2.b32 {%0, %1}, [%2];\n}\n"
+                 : "+r"(d.x), "+r"(d.y)
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(static_cast<int>(v)));
+#else
+    if (v) d = *reinterpret_cast<const uint2*>(p);
+#endif
+}
+GGQ_DEV void ld32k(uint32_t& d, const uint8_t* p, bool v) {
+#ifdef __CUDACC__
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q ld.shared.b32 %0, [%1];\n}\n"
+                 : "+r"(d)
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(static_cast<int>(v)));
+#else
+    if (v) d = *reinterpret_cast<const uint32_t*>(p);
 #endif
 }
 GGQ_DEV uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
@@ -159,6 +177,16 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
     const uint8_t* r1 = r0 + 8 * G::SLOT;
     const uint32_t wrap_sel = (L.t == 3) ? 0x7610u : 0x3210u;
     const int t4 = 4 * L.t;
+    // activation fragments: lanes whose token does not exist keep whatever these hold (their columns are never stored)
+    uint32_t xk[NT][2][2];
+    uint2 xo[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            xk[nt][j][0] = xk[nt][j][1] = 0u;
+            xo[nt][j] = uint2{0u, 0u};
+        }
 #pragma unroll
     for (int p = 0; p < G::PREP_BLOCKS / 2; ++p) {
         if (!FULL && 2 * p >= s.nblk) break;
@@ -183,13 +211,14 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const uint8_t* x = s.xrow[nt] + 2 * kb;
             const float2 c = ld64f(s.tbl + (kb >> 5) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
-            uint32_t bf[2];
-            bf[0] = ld32p(x + 2 * (2 + t4), s.xv[nt]);
-            bf[1] = ld32p(x + 2 * (4 + t4), s.xv[nt]);
+            uint32_t* bf = xk[nt][0];
+            uint32_t* bg = xk[nt][1];
+            ld32k(bf[0], x + 2 * (2 + t4), s.xv[nt]);
+            ld32k(bf[1], x + 2 * (4 + t4), s.xv[nt]);
             mma16816(d, fa, bf, d);
-            bf[0] = ld32p(x + 2 * (18 + t4), s.xv[nt]);
-            bf[1] = ld32p(x + 2 * ((20 + t4) & 31), s.xv[nt]);
-            mma16816(d, fb, bf, d);
+            ld32k(bg[0], x + 2 * (18 + t4), s.xv[nt]);
+            ld32k(bg[1], x + 2 * ((20 + t4) & 31), s.xv[nt]);
+            mma16816(d, fb, bg, d);
             acc.v[nt][0] = fmaf(da_e, d[0], acc.v[nt][0]);
             acc.v[nt][1] = fmaf(da_e, d[1], acc.v[nt][1]);
             acc.v[nt][2] = fmaf(db_e, d[2], acc.v[nt][2]);
@@ -205,13 +234,14 @@ GGQ_DEV void compute_q8_0(const Lane& L, const StageArgs& s, Acc<NT>& acc) {
             const uint8_t* x = s.xrow[nt] + 2 * (kb + 32);
             const float2 c = ld64f(s.tbl + ((kb >> 5) + 1) * (8 * NT) + 8 * nt + 2 * L.t);
             float d[4] = {c.x, c.y, c.x, c.y};
-            uint2 v = ld64p(x + 2 * t4, s.xv[nt]);
-            uint32_t bf[2] = {v.x, v.y};
+            uint2& v = xo[nt][0];
+            uint2& u = xo[nt][1];
+            ld64k(v, x + 2 * t4, s.xv[nt]);
+            const uint32_t bf[2] = {v.x, v.y};
             mma16816(d, fa, bf, d);
-            v = ld64p(x + 2 * (16 + t4), s.xv[nt]);
-            bf[0] = v.x;
-            bf[1] = v.y;
-            mma16816(d, fb, bf, d);
+            ld64k(u, x + 2 * (16 + t4), s.xv[nt]);
+            const uint32_t bg[2] = {u.x, u.y};
+            mma16816(d, fb, bg, d);
             acc.v[nt][0] = fmaf(da_o, d[0], acc.v[nt][0]);
             acc.v[nt][1] = fmaf(da_o, d[1], acc.v[nt][1]);
             acc.v[nt][2] = fmaf(db_o, d[2], acc.v[nt][2]);
@@ -398,10 +428,14 @@ GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) 
     const float zero[4] = {0.f, 0.f, 0.f, 0.f};
     const uint2* xbt = reinterpret_cast<const uint2*>(s.tbl);
     uint4 xek[2][NT], xok[2][NT];
+    uint2 xbk[NT];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) xek[j][nt] = xok[j][nt] = uint4{0u, 0u, 0u, 0u};
+        for (int nt = 0; nt < NT; ++nt) {
+            xek[j][nt] = xok[j][nt] = uint4{0u, 0u, 0u, 0u};
+            xbk[nt] = uint2{0u, 0u};
+        }
 #pragma unroll
     for (int i = 0; i < G::PREP_BLOCKS; ++i) {
         if (!FULL && i >= s.nblk) break;
@@ -419,7 +453,8 @@ GGQ_DEV void compute_q4_k_impl(const Lane& L, const StageArgs& s, Acc<NT>& acc) 
             const int blk = (s.k0 >> 8) + i;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint2 xb = ld64p(reinterpret_cast<const uint8_t*>(xbt + (blk * (8 * NT) + 8 * nt + L.g) * 4 + L.t), s.xv[nt]);
+                uint2& xb = xbk[nt];
+                ld64k(xb, reinterpret_cast<const uint8_t*>(xbt + (blk * (8 * NT) + 8 * nt + L.g) * 4 + L.t), s.xv[nt]);
                 const uint32_t bfr[2] = {xb.x, xb.y};
                 float dm[4];
                 mma16816_bf16(dm, ma, bfr, zero);
@@ -686,6 +721,9 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
     const uint8_t* b1 = r1 + i * G::BLK;
     const uint8_t* sc0 = s.scratch + (i * 16 + L.g) * G::SCRATCH_PER_BLOCK;
     const uint8_t* sc1 = sc0 + 8 * G::SCRATCH_PER_BLOCK;
+    uint2 xk6[NT][2];  // activation fragments; lanes without a token keep whatever these hold
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) xk6[nt][0] = xk6[nt][1] = uint2{0u, 0u};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -707,7 +745,8 @@ GGQ_DEV void compute_q6_k_block(const Lane& L, const StageArgs& s, int i, const 
                 const int j16 = (s.k0 + 256 * i) / 16 + 8 * h + 2 * grp + lh;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const uint2 xv = ld64p(s.xrow[nt] + 2 * kk, s.xv[nt]);
+                    uint2& xv = xk6[nt][grp & 1];
+                    ld64k(xv, s.xrow[nt] + 2 * kk, s.xv[nt]);
                     const float2 c = ld64f(s.tbl + j16 * (8 * NT) + 8 * nt + 2 * L.t);
                     float d[4] = {c.x, c.y, c.x, c.y};
                     const uint32_t bf[2] = {xv.x, xv.y};
