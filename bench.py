@@ -338,6 +338,18 @@ def run_ours(args):
         ms_e2e_graph = timed(torch, dist, g.replay, args.steps, args.warmup, world)
     # kernel alone (no collectives), for the roofline of the dominant kernel
     ms_k = timed(torch, dist, lambda: ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard), args.steps, args.warmup, world)
+    # the same kernel with a device synchronisation between launches: no overlap of one launch's prologue with the
+    # previous launch's drain (programmatic dependent launch), i.e. what ncu's serialised per-launch time corresponds to
+    iso = []
+    for _ in range(12):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ext.mm(ext.FMT_ID[FMT], W, x_dev, rows, T, K, out=c_shard)
+        e1.record()
+        torch.cuda.synchronize()
+        iso.append(e0.elapsed_time(e1))
+    ms_iso = sorted(iso)[len(iso) // 2]
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -368,6 +380,11 @@ def run_ours(args):
                      "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "frac_of_8TBps_nominal": achieved / 8000.0, "us_per_launch": ms_k * 1e3,
                      "algorithmic_bytes_per_launch": k_bytes,
+                     "timing": "CUDA events around the K back-to-back launches of the timed region (launches overlap "
+                               "their prologue with the previous kernel's drain); `isolated` = median of single launches "
+                               "separated by a device synchronisation",
+                     "isolated": {"us_per_launch": ms_iso * 1e3, "achieved": k_bytes / (ms_iso * 1e-3) / 1e9,
+                                  "frac": k_bytes / (ms_iso * 1e-3) / 1e9 / hbm_peak},
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/, N=1 only)
                      "traffic": 297801984 + 6155776 if world == 1 else None,
                      "traffic_source": "ncu --set full, profiles/r1b_decode_q4k_T1_lmhead_ncu_summary.csv (dram read + write bytes of one launch)"},

@@ -77,3 +77,26 @@ def test_entry_points_mirror_the_reference(mod, fn, consts):
     with pytest.raises(ValueError):              # CPU tensors: there is no CPU path
         f(torch.zeros(1 * (K // consts.get("QK8_0", 256)) * (34 if "Q8_0_SIZE" in consts else 1), dtype=torch.int8),
           torch.zeros((1, K), dtype=torch.float16), 1, 1, K)
+
+
+def test_decode_planner_invariants():
+    """ggq_decode_plan is pure host code: every BASELINE decode shape gets a plan that fits one SM's shared memory;
+    shapes whose activations do not fit one CTA are split across a cluster (slices = CTAs per cluster <= 8)."""
+    from kernels import _ext
+    L = _ext.lib()
+    L.ggq_decode_plan.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    L.ggq_decode_plan.restype = ctypes.c_int
+    shapes = [(f, o, t, k) for f in (0, 1, 2) for (o, k) in ((4096, 4096), (14336, 4096), (128256, 4096), (4096, 14336),
+                                                             (28672, 8192), (8192, 28672)) for t in (1, 2, 7, 8, 9, 16)]
+    for f, o, t, k in shapes:
+        out = (ctypes.c_int * 9)()
+        assert L.ggq_decode_plan(f, o, t, k, out) == 0, (f, o, t, k)
+        kw, at, nt, slices, cps, stages, grid_occ, batches, smem = list(out)
+        assert smem <= 227 * 1024 and stages >= 2 and nt == (2 if t > 8 else 1), (f, o, t, k, list(out))
+        assert 1 <= slices <= 8 or at == 4, (f, o, t, k, list(out))
+        qk, cb = ((32, 16), (256, 2), (256, 2))[f]
+        assert slices * cps * cb * qk >= k                       # the slices cover K
+        if t <= 8 and k <= 8192:
+            assert slices == 1 and at == 1, (f, o, t, k, list(out))   # every T <= 8 shape of BASELINE configs[1] is unsliced
+    out = (ctypes.c_int * 9)()
+    assert L.ggq_decode_plan(1, 128256, 1, 4096, out) == 0 and out[5] >= 3   # headline: >= 3 ring stages per warp
