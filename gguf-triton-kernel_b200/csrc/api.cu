@@ -147,6 +147,20 @@ int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const*
     ps.counter_target = sync->counter_base;  // the planner adds the grid size
     ps.rank = sync->rank;
     ps.world = sync->world;
+    ps.epoch_dev = sync->epoch_dev;
+    if (sync->epoch_dev) {  // replayable mode: kernel-maintained epoch, counter starts at 0 every call
+        if (!sync->X_alt) return GGQ_E_POINTER;
+        for (int i = 0; i < n_out; ++i)
+            if (!sync->C_alt[i]) return GGQ_E_POINTER;
+        ps.counter_target = 0;
+        ps.X_alt = static_cast<const uint8_t*>(sync->X_alt);
+        for (int i = 0; i < 8; ++i) ps.alt_out[i] = static_cast<__half*>(sync->C_alt[i < n_out ? i : 0]);
+    }
+    for (int i = 0; i < 8; ++i)
+        ps.x_push[i] = (sync->x_publish && i < sync->world && i != sync->rank) ? static_cast<uint4*>(sync->x_push[i]) : nullptr;
+    if ((ldx & 7) != 0)
+        for (int i = 0; i < 8; ++i)
+            if (ps.x_push[i]) return GGQ_E_SHAPE;  // the push copies whole 16-byte vectors
     a.sync = &ps;
     a.ctas_out = ctas_out;
     if (!decode_supports(fmt, a)) return GGQ_E_FAMILY;

@@ -15,6 +15,10 @@ struct PeerSync {
     uint32_t* x_publish;
     uint32_t epoch, counter_target;
     int rank, world;
+    uint32_t* epoch_dev;      // replayable mode: epoch of a call = *epoch_dev + 1 (kernel-maintained)
+    const uint8_t* X_alt;     // odd epochs read these activations ...
+    __half* alt_out[8];       // ... and store here
+    uint4* x_push[8];         // owner rank: peers' landing buffers for the activations (or null)
 };
 
 struct MmArgs {

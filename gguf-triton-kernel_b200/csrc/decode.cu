@@ -83,12 +83,13 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     // Programmatic dependent launch: the next kernel in the stream may start its own prologue (barrier init, weight
     // prefetch) while this one runs; everything that depends on earlier kernels sits behind pdl_wait() in stage_x.
     pdl_launch_dependents();
+    // cross-GPU exchange: the epoch of this launch (host-supplied, or kernel-maintained in replayable mode, where odd
+    // epochs use the alternate activation / output buffers); settled in stage_x once the previous kernel is complete
+    uint32_t epoch = p.sync.epoch;
+    bool alt = false;
+    uint32_t* epoch_word = reinterpret_cast<uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + MAX_NW;
+    auto out_ptr = [&](int o) -> __half* { return alt ? p.sync.alt_out[o] : p.outs.p[o]; };
     if (tid == 0) {
-        if (p.sync.x_publish != nullptr && blockIdx.x == 0) {
-            // this rank owns the activations (written earlier in stream order): tell the peers they may read them
-            __threadfence_system();
-            st_release_sys(p.sync.x_publish, p.sync.epoch);
-        }
         prefetch_tmap(&map_w);
         mbar_init(&bars[0], 1);
         for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);
@@ -138,8 +139,8 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     if (row < p.O && col < p.T) {
                         const __half h = __float2half_rn(acc[a].v[nt][i]);
                         const int64_t at = col * p.ldc + row;
-                        p.outs.p[0][at] = h;
-                        for (int o = 1; o < p.outs.n; ++o) p.outs.p[o][at] = h;
+                        out_ptr(0)[at] = h;
+                        for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
                     }
                 }
         }
@@ -155,23 +156,61 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         const int e0 = slice * p.cps * G::CHUNK_ELEMS;
         const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
         __syncthreads();  // every warp is done with the previous slice's x / tbl
+        const bool pusher = first && p.sync.x_publish != nullptr && blockIdx.x == 0;  // CTA-uniform
+        if (tid == 0 && first) {
+            pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
+            if (p.sync.epoch_dev != nullptr)  // written back by the last CTA of the previous launch at its very end
+                epoch = *reinterpret_cast<volatile const uint32_t*>(p.sync.epoch_dev) + 1u;
+            *epoch_word = epoch;
+        }
+        if (pusher) {
+            // this rank owns the activations: copy them into every peer's landing buffer, then raise the peers' (local)
+            // ready words -- or, for peers without a landing buffer, this rank's own ready word, which they poll remotely
+            __syncthreads();
+            const uint32_t e = *epoch_word;
+            const uint8_t* const Xsrc = (p.sync.epoch_dev != nullptr && (e & 1u)) ? p.sync.X_alt : p.X;
+            const int vec_per_row = p.K / 8, ld_vec = static_cast<int>(p.ldx_bytes / 16);
+            for (int r = 0; r < p.sync.world; ++r) {
+                uint4* dst = p.sync.x_push[r];
+                if (dst == nullptr) continue;
+                for (int i = tid; i < p.T * vec_per_row; i += NW * 32) {
+                    const int t = i / vec_per_row, c = i - t * vec_per_row;
+                    dst[t * ld_vec + c] = reinterpret_cast<const uint4*>(Xsrc)[t * ld_vec + c];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                bool any_pull = false;
+                for (int r = 0; r < p.sync.world; ++r) {
+                    if (r == p.sync.rank) continue;
+                    if (p.sync.x_push[r] != nullptr) st_release_sys(p.sync.flags_peer[r] + 8, e);
+                    else any_pull = true;
+                }
+                if (any_pull) st_release_sys(p.sync.x_publish, e);
+            }
+        }
         if (tid == 0) {
-            if (first) pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
-            if (p.sync.world > 0 && p.sync.x_ready != nullptr && first) {
-                // activations are produced by rank 0 (peer memory): wait for its "ready" word of this step
-                while (ld_acquire_sys(p.sync.x_ready) < p.sync.epoch) {
+            if (first && p.sync.world > 0 && p.sync.x_ready != nullptr) {
+                // activations come from rank 0: wait for the "ready" word of this step
+                while (ld_acquire_sys(p.sync.x_ready) < epoch) {
                 }
                 fence_proxy_async_all();  // the TMA engine (async proxy) reads what we just acquired
             }
+            const uint8_t* const Xg = (p.sync.epoch_dev != nullptr && (epoch & 1u)) ? p.sync.X_alt : p.X;
             mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
             for (int t = 0; t < p.T; ++t)
-                bulk_g2s(xs + t * p.x_stride, p.X + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
+                bulk_g2s(xs + t * p.x_stride, Xg + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
                          static_cast<uint32_t>(ne * 2), &bars[0]);
         }
         mbar_wait(&bars[0], x_phase);
         x_phase ^= 1;
         stage_activations<FMT, NT, GV>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
         __syncthreads();
+        if (first) {
+            epoch = *epoch_word;
+            alt = p.sync.epoch_dev != nullptr && (epoch & 1u) != 0u;
+        }
     };
 
     // ---- consume the chunk sitting in ring stage `cstage` (chunk `ci` of K-slice `slice`) -----------
@@ -296,8 +335,8 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                     if (row < p.O && col < p.T) {
                         const __half h = __float2half_rn(acc.v[nt][i]);
                         const int64_t at = col * p.ldc + row;
-                        p.outs.p[0][at] = h;
-                        for (int o = 1; o < p.outs.n; ++o) p.outs.p[o][at] = h;
+                        out_ptr(0)[at] = h;
+                        for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
                     }
                 }
         };
@@ -448,18 +487,22 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 
     if (p.sync.world > 1) {
         // ---- fused N-split exchange: every tile above was stored into all ranks' C; tell the peers, wait for theirs
-        __threadfence_system();   // my stores (possibly to peer memory) are ordered before the signal below
-        __syncthreads();
+        __syncthreads();          // all stores of this CTA (possibly to peer memory) are issued ...
         if (tid == 0) {
+            __threadfence_system();   // ... and ordered, at system scope, before the signal below (cumulative over the barrier)
             const uint32_t arrived = atomicAdd(p.sync.counter, 1u) + 1u;
             if (arrived == p.sync.counter_target) {   // last CTA of this rank
                 __threadfence_system();
                 for (int r = 0; r < p.sync.world; ++r)
-                    if (r != p.sync.rank) st_release_sys(p.sync.flags_peer[r] + p.sync.rank, p.sync.epoch);
+                    if (r != p.sync.rank) st_release_sys(p.sync.flags_peer[r] + p.sync.rank, epoch);
                 for (int r = 0; r < p.sync.world; ++r)
                     if (r != p.sync.rank)
-                        while (ld_acquire_sys(p.sync.flags_local + r) < p.sync.epoch) {
+                        while (ld_acquire_sys(p.sync.flags_local + r) < epoch) {
                         }
+                if (p.sync.epoch_dev != nullptr) {  // replayable mode: leave the state ready for the next launch
+                    *p.sync.counter = 0u;
+                    *p.sync.epoch_dev = epoch;
+                }
             }
         }
     }
@@ -517,7 +560,7 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
         const uint32_t xstride = static_cast<uint32_t>(elems * 2 + xpad);
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 127) & ~size_t{127}; return o; };
-        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + 4 * MAX_NW);  // mbarriers + a flag word per warp
+        const size_t o_bars = take(8 * (1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + 4 * MAX_NW + 16);  // mbarriers + a flag word per warp + epoch
         const size_t o_x = take(static_cast<size_t>(T) * xstride);
         const size_t o_tbl = take(elems / G::GROUP * tpad * 4);
         const size_t o_ring = take(static_cast<size_t>(NW) * stages * STAGE_BYTES);
@@ -652,7 +695,7 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
         }
         cfg.gridDim = dim3(S * std::max(1, std::min(max_clusters, pl.grid / S)));
     }
-    if (!(no_pdl || pl.p.sync.world > 1)) {  // not with the in-kernel cross-GPU exchange (spin waits)
+    if (!no_pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

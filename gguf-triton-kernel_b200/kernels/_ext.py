@@ -111,7 +111,8 @@ class PeerSync(ctypes.Structure):
     """ctypes mirror of `ggq_peer_sync` (include/ggq.h)."""
     _fields_ = [("flags_local", _P), ("flags_peer", _P * 8), ("counter", _P), ("x_ready", _P),
                 ("epoch", ctypes.c_uint32), ("counter_base", ctypes.c_uint32), ("rank", ctypes.c_int32),
-                ("world", ctypes.c_int32), ("x_publish", _P)]
+                ("world", ctypes.c_int32), ("x_publish", _P), ("epoch_dev", _P), ("X_alt", _P), ("C_alt", _P * 8),
+                ("x_push", _P * 8)]
 
 
 def mm_sync(fmt: int, A: torch.Tensor, x_ptr: int, outs: list[int], ldc: int, M: int, N: int, K: int,

@@ -100,8 +100,8 @@ class NSplitLinear:
         self._flags.zero_()
         self._fsymm = symm_mem.rendezvous(self._flags, self.group)
         self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._counter_base = 0
-        self._epoch = 0
+        self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # kernel-maintained epoch (replayable mode)
+        self._epoch = 0                                                   # host mirror of it
         torch.cuda.synchronize(dev)
         self._symm.barrier(channel=0)  # everyone's flags are zeroed before anyone signals
         self._prepare_fast_path()
@@ -133,6 +133,21 @@ class NSplitLinear:
             sync.flags_peer[r] = int(self._fsymm.buffer_ptrs[r])
         sync.counter = self._counter.data_ptr()
         sync.rank, sync.world = self.rank, self.world
+        # replayable mode: the kernel keeps the epoch, even epochs use buffer set 0, odd epochs buffer set 1; nothing
+        # in the call changes from step to step, so a step can be captured in a CUDA graph
+        sync.epoch_dev = self._epoch_dev.data_ptr()
+        for i, ptr in enumerate(self._out_ptrs(1)):
+            sync.C_alt[i] = ptr
+        if self.rank == 0:
+            # the owner's kernel pushes the activations into slot 0 of every peer's symmetric buffer and raises word 8
+            # of the peer's flags; the peers poll and read local memory
+            sync.x_publish, sync.x_ready = self._flags.data_ptr() + 8 * 4, 0
+            self._x_even, sync.X_alt = self._x_local[0], self._x_local[1]
+            for r in range(1, self.world):
+                sync.x_push[r] = int(self._xsymm.buffer_ptrs[r])
+        else:
+            sync.x_publish, sync.x_ready = 0, self._flags.data_ptr() + 8 * 4
+            self._x_even = sync.X_alt = self._x_local[0]
         self._sync = sync
         self._sync_ref = ctypes.byref(sync)
         self._ctas = ctypes.c_int(0)
@@ -149,31 +164,43 @@ class NSplitLinear:
         """Rank 0: keep the same activations resident in both symmetric slots (benchmarking `forward(None, T=T)`)."""
         self._xbuf[:, :X.shape[0]].copy_(X)
 
-    def _forward_fused_decode(self, X, T: int, broadcast: bool) -> torch.Tensor:
-        self._epoch += 1
-        cur = self._epoch & 1
-        sync = self._sync
-        sync.x_ready = 0
-        sync.x_publish = 0
-        if broadcast and self.world > 1:
-            if self.rank == 0:
-                if X is not None and X.data_ptr() != self._x_local[cur]:
-                    self._xbuf[cur, :T].copy_(X)          # stream-ordered: lands before the kernel below starts
-                sync.x_publish = self._flag_x_ptr           # the kernel raises the ready word itself
-                x_ptr = self._x_local[cur]
-            else:
-                x_ptr = self._x_rank0[cur]                # rank 0's buffer over NVLink
-                sync.x_ready = self._x_ready_ptr
-        else:
-            x_ptr = X.data_ptr()
-        sync.epoch = self._epoch
-        sync.counter_base = self._counter_base & 0xFFFFFFFF
-        rc = self._lib.ggq_mm_sync(self._fmt_id, self._a_ptr, x_ptr, self.K, self._out_arr[cur], self.world, self.O, self.per,
-                                   T, self.K, self._sync_ref, self._ctas_ref, torch.cuda.current_stream().cuda_stream)
+    def _launch_sync(self, T: int) -> None:
+        """One fused step with the activations in the symmetric buffer of rank 0 (static arguments: graph-capturable)."""
+        rc = self._lib.ggq_mm_sync(self._fmt_id, self._a_ptr, self._x_even, self.K, self._out_arr[0], self.world, self.O,
+                                   self.per, T, self.K, self._sync_ref, self._ctas_ref,
+                                   torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             self._ext.check(rc, "ggq_mm_sync")
-        self._counter_base += self._ctas.value
+
+    def _forward_fused_decode(self, X, T: int, broadcast: bool) -> torch.Tensor:
+        if not (broadcast and self.world > 1):
+            raise ValueError("the fused decode path takes its activations from rank 0 (broadcast=True, world > 1)")
+        self._epoch += 1
+        cur = self._epoch & 1
+        if self.rank == 0 and X is not None and X.data_ptr() != self._x_local[cur]:
+            self._xbuf[cur, :T].copy_(X)              # stream-ordered: lands before the kernel below starts
+        self._launch_sync(T)
         return self._out[cur, :T]
+
+    def capture_steps(self, T: int, n: int):
+        """CUDA graph of `n` consecutive fused decode steps on the activations resident in rank 0's symmetric buffer
+        (set_resident_input / input_buffer).  Returns replay(): every rank must replay the same number of times;
+        last_output(T) is the result of the last step."""
+        if not (self.mode == "fused" and self.world > 1 and T <= 16 and self.per >= 16):
+            raise ValueError("capture_steps needs the fused decode path")
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                self._launch_sync(T)
+
+        def replay():
+            g.replay()
+            self._epoch += n
+        return replay
+
+    def last_output(self, T: int) -> torch.Tensor:
+        return self._out[self._epoch & 1, :T]
 
     def forward(self, X, *, broadcast: bool = True, T: int | None = None) -> torch.Tensor:
         """X: fp16 [T, K] (valid on rank 0 when `broadcast`; None + T = the activations were written into
@@ -182,7 +209,7 @@ class NSplitLinear:
         if self.mode == "fused":
             if T > self.max_tokens:
                 raise ValueError(f"T={T} exceeds max_tokens={self.max_tokens} of the symmetric buffer")
-            if T <= 16 and self.per >= 16:
+            if T <= 16 and self.per >= 16 and broadcast and self.world > 1:
                 return self._forward_fused_decode(X, T, broadcast)
             if broadcast and self.world > 1:
                 dist.broadcast(X, src=0, group=self.group)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 101 /* 0.1.1 */
+#define GGQ_VERSION 103 /* 0.1.3 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -104,6 +104,19 @@ typedef struct ggq_peer_sync {
     uint32_t* x_publish; /* rank that OWNS the activations: its "ready" word (the one the peers pass as x_ready); the
                             kernel stores `epoch` there when it starts (the activations were written earlier in
                             stream order), so no separate flag kernel is needed.  NULL on the other ranks. */
+    /* Replayable mode (epoch_dev != NULL): nothing in the call changes from step to step, so the launch can be
+     * captured in a CUDA graph and replayed.  `epoch` and `counter_base` are ignored: the epoch of a call is
+     * *epoch_dev + 1, read by the kernel; the last CTA writes it back and resets *counter to 0 when the exchange is
+     * complete.  Calls with an EVEN epoch use (X, C_out), calls with an ODD epoch use (X_alt, C_alt): the output
+     * double buffering that keeps a fast rank from overwriting results a slow rank's consumer is still reading. */
+    uint32_t* epoch_dev;   /* device word, zero-initialised, local to this rank */
+    const void* X_alt;
+    void* C_alt[8];
+    /* Owner rank only (x_publish != NULL), optional: peer-mapped [T, ldx] landing buffers of the other ranks, indexed
+     * like flags_peer (own entry ignored).  When x_push[r] is set the owner's kernel COPIES the activations into rank
+     * r's buffer and then raises word 8 of rank r's flags array, so rank r passes its own local buffer as X and its own
+     * flags_local + 8 as x_ready: it polls and reads local memory instead of crossing NVLink twice. */
+    void* x_push[8];
 } ggq_peer_sync;
 
 /* Returns 0 and writes the number of CTAs launched to *ctas_out (the caller advances counter_base by it). */

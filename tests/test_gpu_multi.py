@@ -37,7 +37,21 @@ def _worker(rank, world, port, fmt, O, T, K, mode, q):
         torch.cuda.synchronize()
         diff = (C.float() - full.float()).abs().max().item()
         scale = full.float().abs().max().item()
-        q.put((rank, C.shape == (T, O) and diff <= 2e-3 * scale, diff, scale))
+        ok = C.shape == (T, O) and diff <= 2e-3 * scale
+        if mode == "fused" and T <= 16:
+            # the fused decode step replayed from a CUDA graph (kernel-maintained epoch), then an eager step again
+            if rank == 0:
+                layer.set_resident_input(X)
+            torch.cuda.synchronize()
+            td.barrier()
+            replay = layer.capture_steps(T, 4)
+            for _ in range(3):
+                replay()
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(layer.last_output(T), C)
+            ok = ok and torch.equal(layer.forward(X), C)
+            torch.cuda.synchronize()
+        q.put((rank, ok, diff, scale))
         td.destroy_process_group()
     except Exception as e:  # noqa: BLE001
         q.put((rank, False, repr(e), 0.0))
@@ -54,7 +68,12 @@ def test_nsplit_two_gpus(mode, fmt, O, T, K):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, fmt, O, T, K, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        res = [q.get(timeout=180) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:   # never leave a rank spinning on the GPU
+            if p.is_alive():
+                p.kill()
     assert all(r[1] is True for r in res), res
