@@ -50,6 +50,7 @@ struct Params {
     int n_slices;
     int num_batches;
     int stages;
+    int bulk_push;         // fused exchange: copy the CTA's finished rows to the peers in 16-byte vectors at the end
     int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
     PeerSync sync;      // world == 0: no cross-GPU synchronisation
     uint32_t x_stride;  // bytes between token rows in shared memory
@@ -156,7 +157,11 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         const int e0 = slice * p.cps * G::CHUNK_ELEMS;
         const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
         __syncthreads();  // every warp is done with the previous slice's x / tbl
-        const bool pusher = first && p.sync.x_publish != nullptr && blockIdx.x == 0;  // CTA-uniform
+        // owner rank: CTA b < world serves peer b (copies the activations into its landing buffer, then raises its ready
+        // word), so the pushes to all peers run in parallel; CTA `rank` raises the word that peers without a landing
+        // buffer poll remotely.  (The grid has >= world CTAs whenever there are >= world tiles; else CTA 0 serves all.)
+        const int nserve = min(static_cast<int>(gridDim.x), p.sync.world);
+        const bool pusher = first && p.sync.x_publish != nullptr && static_cast<int>(blockIdx.x) < nserve;  // CTA-uniform
         if (tid == 0 && first) {
             pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
             if (p.sync.epoch_dev != nullptr)  // written back by the last CTA of the previous launch at its very end
@@ -164,30 +169,30 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             *epoch_word = epoch;
         }
         if (pusher) {
-            // this rank owns the activations: copy them into every peer's landing buffer, then raise the peers' (local)
-            // ready words -- or, for peers without a landing buffer, this rank's own ready word, which they poll remotely
             __syncthreads();
             const uint32_t e = *epoch_word;
             const uint8_t* const Xsrc = (p.sync.epoch_dev != nullptr && (e & 1u)) ? p.sync.X_alt : p.X;
             const int vec_per_row = p.K / 8, ld_vec = static_cast<int>(p.ldx_bytes / 16);
+            const bool all = nserve < p.sync.world;   // too few CTAs: CTA 0 serves every peer
             for (int r = 0; r < p.sync.world; ++r) {
+                if (!all && r != static_cast<int>(blockIdx.x)) continue;
+                if (all && blockIdx.x != 0) continue;
                 uint4* dst = p.sync.x_push[r];
-                if (dst == nullptr) continue;
-                for (int i = tid; i < p.T * vec_per_row; i += NW * 32) {
-                    const int t = i / vec_per_row, c = i - t * vec_per_row;
-                    dst[t * ld_vec + c] = reinterpret_cast<const uint4*>(Xsrc)[t * ld_vec + c];
-                }
+                if (dst != nullptr)
+                    for (int i = tid; i < p.T * vec_per_row; i += NW * 32) {
+                        const int t = i / vec_per_row, c = i - t * vec_per_row;
+                        dst[t * ld_vec + c] = reinterpret_cast<const uint4*>(Xsrc)[t * ld_vec + c];
+                    }
             }
             __syncthreads();
             if (tid == 0) {
                 __threadfence_system();
-                bool any_pull = false;
                 for (int r = 0; r < p.sync.world; ++r) {
-                    if (r == p.sync.rank) continue;
-                    if (p.sync.x_push[r] != nullptr) st_release_sys(p.sync.flags_peer[r] + 8, e);
-                    else any_pull = true;
+                    if (!all && r != static_cast<int>(blockIdx.x)) continue;
+                    if (all && blockIdx.x != 0) continue;
+                    if (r == p.sync.rank) st_release_sys(p.sync.x_publish, e);   // for peers that pull
+                    else if (p.sync.x_push[r] != nullptr) st_release_sys(p.sync.flags_peer[r] + 8, e);
                 }
-                if (any_pull) st_release_sys(p.sync.x_publish, e);
             }
         }
         if (tid == 0) {
@@ -336,7 +341,8 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                         const __half h = __float2half_rn(acc.v[nt][i]);
                         const int64_t at = col * p.ldc + row;
                         out_ptr(0)[at] = h;
-                        for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
+                        if (!p.bulk_push)
+                            for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
                     }
                 }
         };
@@ -431,6 +437,23 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             }
         }
         if (S > 1) cl_sync();  // nobody writes into the shared memory of a CTA that has exited
+        if (p.bulk_push && p.outs.n > 1) {
+            // fused N-split exchange: this CTA's rows [tile_lo*16, tile_hi*16) of every token are complete in the local
+            // buffer; copy them to the peers as whole 16-byte vectors (an NVLink packet per 128 contiguous bytes instead
+            // of one per 8 rows: the per-tile 2-byte peer stores made the 8-GPU step packet-rate bound)
+            __syncthreads();
+            const int row0 = tile_lo * 16;
+            const int nrows = min(tile_hi * 16, static_cast<int>(p.O)) - row0;
+            const int nvec = nrows / 8;
+            for (int o = 1; o < p.outs.n; ++o)
+                for (int t = 0; t < p.T; ++t) {
+                    const __half* src = out_ptr(0) + t * p.ldc + row0;
+                    __half* dst = out_ptr(o) + t * p.ldc + row0;
+                    for (int i = tid; i < nvec; i += NW * 32)
+                        reinterpret_cast<uint4*>(dst)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
+                    for (int i = nvec * 8 + tid; i < nrows; i += NW * 32) dst[i] = __ldcg(src + i);
+                }
+        }
     } else {
         // ======== K-sliced walk: AT live tiles per warp share each staged activation slice ========
         auto tile_of = [&](int batch, int a) -> int64_t {
@@ -540,6 +563,7 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.nw = NW;
     pl.occ = OCC;
     if (a.sync) p.sync = *a.sync;
+    p.bulk_push = 0;
     {
         static const int skip = [] { const char* e = getenv("GGQ_DECODE_NOCOMPUTE"); return (e && e[0] == '1') ? 1 : 0; }();
         p.dbg_skip_compute = skip;
@@ -604,6 +628,14 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
     if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA / cluster owns >= 1 tile
+        if (a.sync && a.n_out > 1 && a.ldc % 8 == 0 && !getenv("GGQ_NO_BULK_PUSH")) {
+            bool aligned = true;
+            for (int i = 0; i < a.n_out; ++i) {
+                aligned = aligned && (reinterpret_cast<uintptr_t>(a.C[i]) & 15) == 0;
+                if (a.sync->epoch_dev) aligned = aligned && (reinterpret_cast<uintptr_t>(a.sync->alt_out[i]) & 15) == 0;
+            }
+            p.bulk_push = aligned ? 1 : 0;
+        }
         p.KW = 1;
         pl.grid = S * std::max(1, std::min(sms / S, p.num_tiles));
         p.num_batches = 1;
