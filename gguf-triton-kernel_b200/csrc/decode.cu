@@ -90,14 +90,19 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     bool alt = false;
     uint32_t* epoch_word = reinterpret_cast<uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + MAX_NW;
     auto out_ptr = [&](int o) -> __half* { return alt ? p.sync.alt_out[o] : p.outs.p[o]; };
-    if (tid == 0) {
-        prefetch_tmap(&map_w);
-        mbar_init(&bars[0], 1);
-        for (int i = 0; i < NW * STG; ++i) mbar_init(&bars[1 + i], 1);
-        for (int i = 0; i < 2 * MAX_NW; ++i) mbar_init(&bars[1 + MAX_NW * MAX_STAGES + i], 1);  // cluster mailboxes
+    // every warp initialises its own barriers (ring stages, cluster mailbox pair) and starts streaming right away; the
+    // barrier of the activations (bars[0], warp 0) is first used after the __syncthreads at the top of stage_x
+    if (lane == 0) {
+        if (w == 0) {
+            prefetch_tmap(&map_w);
+            mbar_init(&bars[0], 1);
+        }
+        for (int s = 0; s < STG; ++s) mbar_init(my_full + s, 1);
+        mbar_init(&bars[1 + MAX_NW * MAX_STAGES + w], 1);            // cluster mailbox: filled
+        mbar_init(&bars[1 + MAX_NW * MAX_STAGES + MAX_NW + w], 1);   // cluster mailbox: free
         fence_mbar_init();
     }
-    __syncthreads();
+    __syncwarp();
 
     const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
     // live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA

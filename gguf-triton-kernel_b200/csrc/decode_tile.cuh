@@ -623,6 +623,31 @@ GGQ_DEV void compute_q4_k_gv_impl(const Lane& L, const StageArgs& s, Acc<1>& acc
         for (int c = 0; c < 4; ++c) {
             const uint2 wa = ld64(q0 + 32 * c), wb = ld64(q1 + 32 * c);
             uint32_t e1f[4], e2f[4], o1f[4], o2f[4];
+            float de[4], dd[4];
+#ifndef GGQ_Q4K_NO_BYTEFRAG
+            // odd sub-block through whole BYTES (16 * hi + lo) * 2^-24: one PRMT replaces a shift and a mask per word; the
+            // low-nibble cross term it drags in is exactly de[odd column], which this lane already holds
+            const uint32_t ta = prmt(wa.x, 0u, 0x4341), tb = prmt(wb.x, 0u, 0x4341);
+            const uint32_t ua = prmt(wa.y, 0u, 0x4341), ub = prmt(wb.y, 0u, 0x4341);
+            e1f[0] = wa.x & 0x000F000Fu;  e1f[2] = ta & 0x000F000Fu;
+            e1f[1] = wb.x & 0x000F000Fu;  e1f[3] = tb & 0x000F000Fu;
+            o1f[0] = wa.x & 0x00FF00FFu;  o1f[2] = ta;
+            o1f[1] = wb.x & 0x00FF00FFu;  o1f[3] = tb;
+            e2f[0] = wa.y & 0x000F000Fu;  e2f[2] = ua & 0x000F000Fu;
+            e2f[1] = wb.y & 0x000F000Fu;  e2f[3] = ub & 0x000F000Fu;
+            o2f[0] = wa.y & 0x00FF00FFu;  o2f[2] = ua;
+            o2f[1] = wb.y & 0x00FF00FFu;  o2f[3] = ub;
+            mma16816(de, e1f, b1, zero);
+            mma16816(de, e2f, b2, de);
+            mma16816(dd, o1f, b1, zero);
+            mma16816(dd, o2f, b2, dd);
+            if (L.t == c) {  // columns 2c (sub-block 2c) and 2c + 1 live in this lane
+                a0 = fmaf(ca.x, de[0], a0);
+                a2 = fmaf(cb.x, de[2], a2);
+                a1 = fmaf(ca.y, dd[1] - de[1], a1);
+                a3 = fmaf(cb.y, dd[3] - de[3], a3);
+            }
+#else
             e1f[0] = wa.x & 0x000F000Fu;  e1f[2] = (wa.x >> 8) & 0x000F000Fu;
             o1f[0] = wa.x & 0x00F000F0u;  o1f[2] = (wa.x >> 8) & 0x00F000F0u;
             e1f[1] = wb.x & 0x000F000Fu;  e1f[3] = (wb.x >> 8) & 0x000F000Fu;
@@ -631,7 +656,6 @@ GGQ_DEV void compute_q4_k_gv_impl(const Lane& L, const StageArgs& s, Acc<1>& acc
             o2f[0] = wa.y & 0x00F000F0u;  o2f[2] = (wa.y >> 8) & 0x00F000F0u;
             e2f[1] = wb.y & 0x000F000Fu;  e2f[3] = (wb.y >> 8) & 0x000F000Fu;
             o2f[1] = wb.y & 0x00F000F0u;  o2f[3] = (wb.y >> 8) & 0x00F000F0u;
-            float de[4], dd[4];
             mma16816(de, e1f, b1, zero);
             mma16816(de, e2f, b2, de);
             mma16816(dd, o1f, b1, zero);
@@ -642,6 +666,7 @@ GGQ_DEV void compute_q4_k_gv_impl(const Lane& L, const StageArgs& s, Acc<1>& acc
                 a1 = fmaf(ca.y, dd[1], a1);
                 a3 = fmaf(cb.y, dd[3], a3);
             }
+#endif
         }
     }
     acc.v[0][0] = a0;
