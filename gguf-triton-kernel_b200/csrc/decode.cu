@@ -1,22 +1,27 @@
 // decode.cu — HBM-bound skinny GEMM (T <= 16 tokens per pass): C[T, O] = X[T, K] . dequant(W)[O, K]^T
 //
-// Persistent kernel, one CTA per SM, NW consumer warps, no dedicated producer: every warp runs its
-// OWN ring of TMA bulk copies (cp.async.bulk + mbarrier complete_tx) over the packed bytes of the
-// 16-row tiles it owns, so there is no cross-warp synchronisation on the weight stream at all:
+// Persistent kernel (12 warps per SM, or two 8-warp CTAs), no dedicated producer: every warp runs its OWN ring of 2-D
+// TMA boxes (cp.async.bulk.tensor + mbarrier complete_tx) over the packed bytes of 16-row tiles, so there is no
+// cross-warp synchronisation on the weight stream at all:
 //
-//     for each of my (tile, k-chunk) items:   wait(full[stage]) -> prep scales -> 16x{8,16} MMA tile
+//     for each of my (tile, k-chunk) items:   wait(full[stage]) -> prep scales -> 16 x {8,16} MMA tile
 //                                             -> re-arm the stage with the item STAGES ahead
 //
-// A stage holds CHUNK_BLOCKS blocks of each of the tile's 16 rows (16 bulk copies of 420..576 B,
-// issued by 16 lanes); rows are copied verbatim, 16-byte aligned supersets where a chunk starts
-// mid-vector (Q6_K).  Activations are staged once per K-slice as raw fp16 rows, also by bulk copy,
-// plus a table of per-block activation sums that cancels the integer->fp16 bias (decode_tile.cuh).
+// A stage holds one chunk (Geo<FMT>::CHUNK_BLOCKS blocks) of each of the tile's 16 rows, copied verbatim (16-byte
+// aligned supersets where a chunk starts mid-vector, Q6_K).  Activations are staged once as raw fp16 rows by bulk
+// copy, plus a table of per-sub-block activation sums that cancels the integer->fp16 bias (decode_tile.cuh).
 //
-// Work decomposition (all static, chosen on the host):
-//   KW  warps cooperating on one tile (split over K chunks, reduced through shared memory) — 1 when
-//       there are at least as many tiles as warps on the GPU, up to 8 for small O
-//   AT  tiles whose accumulators a warp keeps live while the CTA walks the K-slices (4 when the
-//       activations of all tokens do not fit in shared memory at once, else 1)
+// Work decomposition (static, chosen on the host, `ggq_decode_plan`):
+//   * single K-slice (the activations of all tokens fit next to the rings): CTA c owns a contiguous range of tiles and
+//     its tiles x chunks items are cut into NW equal ranges, one per warp; a tile cut by a range boundary is finished
+//     by the warp holding its head, the others park their partial sums in shared memory and raise a flag;
+//   * otherwise clusters of S = 2..8 CTAs split K: CTA r stages K-slice r of the activations, partial sums travel
+//     rank S-1 -> ... -> 0 through per-warp DSMEM mailboxes (st.async + mbarrier);
+//   * last resort: K-slices staged one after the other with AT = 4 live tiles per warp and KW warps per tile.
+// T == 1 uses the GEMV tile code (`GV`): the 8 MMA columns carry 8 sub-blocks instead of 8 tokens.
+// Launches use programmatic stream serialization: the prologue and the weight prefetch of a launch overlap the drain
+// of the previous kernel; `griddepcontrol.wait` sits in front of the first access to the activations.
+// With a `ggq_peer_sync` the kernel also does the N-split exchange (activation push, peer stores, epoch flags).
 // HBM traffic = packed weight bytes once (+ <= 3 % activations/outputs); roofline: HBM bandwidth.
 #include <cstring>
 #include <algorithm>
@@ -105,7 +110,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     __syncwarp();
 
     const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
-    // live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA
+    // (K-sliced fallback) live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA
     // ---- epilogue of one batch: (reduce over the KW warps of a tile,) round to fp16, store ------------
     auto epilogue = [&](Acc<NT>* acc, int batch) {
         if constexpr (GV) gemv_finalize(acc[0]);
@@ -633,7 +638,8 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
     if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA / cluster owns >= 1 tile
-        if (a.sync && a.n_out > 1 && a.ldc % 8 == 0 && !getenv("GGQ_NO_BULK_PUSH")) {
+        static const bool no_bulk = getenv("GGQ_NO_BULK_PUSH") != nullptr;
+        if (a.sync && a.n_out > 1 && a.ldc % 8 == 0 && !no_bulk) {
             bool aligned = true;
             for (int i = 0; i < a.n_out; ++i) {
                 aligned = aligned && (reinterpret_cast<uintptr_t>(a.C[i]) & 15) == 0;
@@ -659,7 +665,8 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
 // CTA per SM with the full 227 KB (activations of many tokens / K-slicing).
 template <int FMT>
 static bool make_plan(const MmArgs& a, int T, Plan& pl) {
-    if (const char* f = getenv("GGQ_PLAN_FORCE")) {  // dev: "8,2" | "12,1" | "8,1"
+    static const char* const force = getenv("GGQ_PLAN_FORCE");  // dev: "nw,occ[,cluster]", e.g. "8,2" | "12,1" | "8,1,2"
+    if (const char* f = force) {
         const int nw = atoi(f), occ = (strchr(f, ',') ? atoi(strchr(f, ',') + 1) : 1);
         const char* c2 = strchr(f, ',') ? strchr(strchr(f, ',') + 1, ',') : nullptr;
         const int S = c2 ? atoi(c2 + 1) : 1;
@@ -670,7 +677,8 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 2) return true;
     if (make_plan_cfg<FMT>(a, T, 8, 1, false, pl) && pl.p.stages >= 2) return true;
     // the activations of all tokens do not fit in one CTA: clusters of 2 / 4 / 8 CTAs split K (and the activations)
-    if (!getenv("GGQ_NO_CLUSTER")) {
+    static const bool no_cluster = getenv("GGQ_NO_CLUSTER") != nullptr;
+    if (!no_cluster) {
         // smallest padding of K first (S * cps chunks are walked for nc real ones), then the smaller cluster (fewer
         // hops, and small clusters tile the GPCs without leaving SMs idle), then 12 warps before 8
         int best_s = 0, best_nw = 0, best_waste = 1 << 30;
@@ -702,12 +710,33 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         configured_dev_mask[dev] = 1;
     }
-    // the packed rows viewed as int32 [O, rowB / 4]; box = 16 rows x SLOT bytes
-    alignas(64) CUtensorMap map_w;
-    if (!make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_INT32, pl.p.W, static_cast<uint64_t>(pl.p.rowB / 4),
-                     static_cast<uint64_t>(pl.p.O), static_cast<uint64_t>(pl.p.rowB), Geo<FMT>::SLOT / 4, 16,
-                     CU_TENSOR_MAP_SWIZZLE_NONE))
-        return static_cast<int>(cudaErrorInvalidValue);
+    // the packed rows viewed as int32 [O, rowB / 4]; box = 16 rows x SLOT bytes.  Encoding a map costs ~1 us of host
+    // time, as much as the rest of the call: the last few (weight pointer, shape) maps of this thread are kept.
+    struct MapSlot {
+        const void* w;
+        int64_t rowB, O;
+        int dev;
+        alignas(64) CUtensorMap map;
+    };
+    static thread_local MapSlot cache[8] = {};
+    static thread_local unsigned next_slot = 0;
+    const CUtensorMap* found = nullptr;
+    for (const MapSlot& c : cache)
+        if (c.w == pl.p.W && c.rowB == pl.p.rowB && c.O == pl.p.O && c.dev == dev && c.w != nullptr) found = &c.map;
+    if (!found) {
+        MapSlot& c = cache[next_slot++ % 8];
+        c.w = nullptr;
+        if (!make_map_2d(&c.map, CU_TENSOR_MAP_DATA_TYPE_INT32, pl.p.W, static_cast<uint64_t>(pl.p.rowB / 4),
+                         static_cast<uint64_t>(pl.p.O), static_cast<uint64_t>(pl.p.rowB), Geo<FMT>::SLOT / 4, 16,
+                         CU_TENSOR_MAP_SWIZZLE_NONE))
+            return static_cast<int>(cudaErrorInvalidValue);
+        c.w = pl.p.W;
+        c.rowB = pl.p.rowB;
+        c.O = pl.p.O;
+        c.dev = dev;
+        found = &c.map;
+    }
+    const CUtensorMap& map_w = *found;
     static const bool no_pdl = getenv("GGQ_NO_PDL") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
@@ -755,7 +784,8 @@ static int launch_fmt(const MmArgs& a) {
         Plan pl;
         if (!make_plan<FMT>(s, T, pl)) return GGQ_E_FAMILY;
         int rc;
-        if (T == 1 && pl.at == 1 && pl.p.n_slices == 1 && !getenv("GGQ_NO_GEMV")) {  // single token: GEMV tile code
+        static const bool no_gemv = getenv("GGQ_NO_GEMV") != nullptr;
+        if (T == 1 && pl.at == 1 && pl.p.n_slices == 1 && !no_gemv) {  // single token: GEMV tile code
             rc = pl.occ == 2   ? launch_kernel<FMT, 1, 1, 8, 2, true>(pl, a.stream)
                  : pl.nw == 12 ? launch_kernel<FMT, 1, 1, 12, 1, true>(pl, a.stream)
                                : launch_kernel<FMT, 1, 1, 8, 1, true>(pl, a.stream);

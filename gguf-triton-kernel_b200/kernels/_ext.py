@@ -76,6 +76,15 @@ def _check_operands(fmt: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, 
         raise ValueError(f"B has {B.numel()} elements, expected N*K={N * K}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # cudaStream_t of a device's current stream
+
+
+def _current_stream(index: int) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(index)
+    return torch.cuda.current_stream(index).cuda_stream
+
+
 def mm(fmt: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, family: int = FAMILY_AUTO,
        out: torch.Tensor | None = None) -> torch.Tensor:
     """C[N, M] (fp16) = B[N, K] @ dequant(A)[M, K]^T on A's device, current stream, asynchronous."""
@@ -84,15 +93,24 @@ def mm(fmt: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, fa
     if out is not None and (out.dtype != torch.float16 or out.shape != (N, M) or not out.is_contiguous()
                             or out.device != A.device):
         raise ValueError("out must be a contiguous float16 [N, M] tensor on A's device")
-    with torch.cuda.device(A.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    index = A.device.index
+    L = lib()
+
+    def launch() -> int:
+        stream = _current_stream(index)
         if family == FAMILY_AUTO:
-            fn = (lib().ggq_mm_q8_0_f16, lib().ggq_mm_q4_k_f16, lib().ggq_mm_q6_k_f16)[fmt]
-            rc = fn(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, stream)
-        else:
-            outs = (_P * 1)(C.data_ptr())
-            rc = lib().ggq_mm_ex(fmt, A.data_ptr(), B.data_ptr(), K, outs, 1, M, M, N, K, family, stream)
-    check(rc, "ggq_mm")
+            fn = (L.ggq_mm_q8_0_f16, L.ggq_mm_q4_k_f16, L.ggq_mm_q6_k_f16)[fmt]
+            return fn(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, stream)
+        outs = (_P * 1)(C.data_ptr())
+        return L.ggq_mm_ex(fmt, A.data_ptr(), B.data_ptr(), K, outs, 1, M, M, N, K, family, stream)
+
+    if torch.cuda.current_device() == index:   # the common case: no device switch (the guard costs microseconds)
+        rc = launch()
+    else:
+        with torch.cuda.device(index):
+            rc = launch()
+    if rc != 0:
+        check(rc, "ggq_mm")
     return C
 
 
