@@ -401,8 +401,8 @@ def run_ours(args):
                      "isolated": {"us_per_launch": ms_iso * 1e3, "achieved": k_bytes / (ms_iso * 1e-3) / 1e9,
                                   "frac": k_bytes / (ms_iso * 1e-3) / 1e9 / hbm_peak},
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/, N=1 only)
-                     "traffic": 297801984 + 6155776 if world == 1 else None,
-                     "traffic_source": "ncu --set full, profiles/r1b_decode_q4k_T1_lmhead_ncu_summary.csv (dram read + write bytes of one launch)"},
+                     "traffic": 297782784 + 5429248 if world == 1 else None,
+                     "traffic_source": "ncu --set full, profiles/r1c_decode_q4k_T1_lmhead_ncu_summary.csv (dram read + write bytes of one launch)"},
         "cpu_baseline": {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_rows} of {O} rows, one pass ({cpu_dt:.1f} s), numpy oracle port of kernels/cpu_impls"},
         "parity": parity,
