@@ -908,6 +908,54 @@ template <int FMT, int NT, bool GV = false>
 GGQ_DEV void stage_activations(uint8_t* xs, uint32_t x_stride, float* tbl, int ne, int T, int tid, int nthreads) {
     using G = Geo<FMT>;
     constexpr int TPAD = 8 * NT;
+#ifdef __CUDACC__
+    if (FMT == 1) {
+        // Q4_K on the device: one 16-byte vector (8 activations) per thread and step -- permute it in place, add its 8
+        // values, fold the 4 vectors of a 32-activation sub-block with two shuffles.  (The host emulator keeps the
+        // one-thread-per-64-activations form below; the sums differ in the last bits only.)  `ne` is a multiple of 256,
+        // so a warp is always entirely inside or entirely outside the T * ne / 8 vectors.
+        const int vpr = ne / 8, total = T * vpr, lane = tid & 31;
+        uint2* xb = reinterpret_cast<uint2*>(tbl);
+        for (int idx = tid; idx < total; idx += nthreads) {
+            const int tok = idx / vpr, v = idx - tok * vpr;
+            uint4* ptr = reinterpret_cast<uint4*>(xs + tok * x_stride) + v;
+            const uint4 q = *ptr;
+            float sum = h2f(q.x & 0xffffu);
+            sum += h2f(q.x >> 16);
+            sum += h2f(q.y & 0xffffu);
+            sum += h2f(q.y >> 16);
+            sum += h2f(q.z & 0xffffu);
+            sum += h2f(q.z >> 16);
+            sum += h2f(q.w & 0xffffu);
+            sum += h2f(q.w >> 16);
+            uint4 o;  // (x0 x1 x2 x3) -> (x0 x2 x1 x3), per group of four
+            o.x = prmt(q.x, q.y, 0x5410);
+            o.y = prmt(q.x, q.y, 0x7632);
+            o.z = prmt(q.z, q.w, 0x5410);
+            o.w = prmt(q.z, q.w, 0x7632);
+            *ptr = o;
+            sum += shfl_xor(sum, 1);
+            sum += shfl_xor(sum, 2);               // sum of sub-block v / 4
+            const float other = shfl_xor(sum, 4);  // ... and of its neighbour in the 64-activation pair
+            if (GV) {
+                if ((lane & 3) == 0) tbl[v >> 2] = sum;
+            } else if ((lane & 7) == 0) {
+                const int e = v >> 3, b = e >> 2, t = e & 3;
+                const uint32_t h0 = f2u(sum) & 0xffff0000u, h1 = f2u(other) & 0xffff0000u;  // bf16 hi (truncated), lo = rest
+                const uint32_t l0 = bf16_bits_rn(sum - u2f(h0)), l1 = bf16_bits_rn(other - u2f(h1));
+                xb[(b * TPAD + tok) * 4 + t] = uint2{(h0 >> 16) | h1, l0 | (l1 << 16)};
+            }
+        }
+        if (!GV) {  // token columns that do not exist read as zero
+            const int nent = ne / 64;
+            for (int idx = tid; idx < nent * (TPAD - T); idx += nthreads) {
+                const int e = idx % nent, col = T + idx / nent;
+                xb[((e >> 2) * TPAD + col) * 4 + (e & 3)] = uint2{0u, 0u};
+            }
+        }
+        return;
+    }
+#endif
     if (FMT == 1 && GV) {  // one token: tbl[sub-block] = fp32 sum of its 32 activations
         for (int e = tid; e < ne / 64; e += nthreads) q4k_stage_pair_gv(xs + e * 128, tbl + 2 * e);
     } else if (GV) {       // one token: tbl[group] = TBL_MUL * sum of its GROUP activations
