@@ -112,8 +112,8 @@ class NSplitLinear:
         return [ptrs[self.rank]] + [p for i, p in enumerate(ptrs) if i != self.rank]
 
     def _prepare_fast_path(self):
-        """Everything that does not change from step to step is built once: the per-step host cost of the fused
-        path is a handful of attribute writes and one ctypes call (the kernels take ~15-70 us)."""
+        """Everything about a fused decode step is fixed here, once: a step is one ctypes call with the same arguments
+        every time (the kernel keeps the exchange epoch), which is also what makes it CUDA-graph capturable."""
         import ctypes
         ext = self._ext
         self._lib = ext.lib()
@@ -125,8 +125,6 @@ class NSplitLinear:
         self._out_arr = [(ctypes.c_void_p * self.world)(*self._out_ptrs(c)) for c in (0, 1)]
         xrows = self._xbuf.shape[1]
         self._x_local = [self._xbuf.data_ptr() + c * xrows * self.K * 2 for c in (0, 1)]
-        self._x_rank0 = [int(self._xsymm.buffer_ptrs[0]) + c * xrows * self.K * 2 for c in (0, 1)]
-        self._x_ready_ptr = int(self._fsymm.buffer_ptrs[0]) + 8 * 4
         sync = ext.PeerSync()
         sync.flags_local = self._flags.data_ptr()
         for r in range(self.world):
@@ -153,7 +151,6 @@ class NSplitLinear:
         self._ctas = ctypes.c_int(0)
         self._ctas_ref = ctypes.byref(self._ctas)
         self._a_ptr = self.A.data_ptr()
-        self._flag_x_ptr = self._flags.data_ptr() + 8 * 4   # rank 0's "activations of epoch e are in place" word
 
     def input_buffer(self, T: int) -> torch.Tensor:
         """Rank 0: the symmetric [T, K] buffer the NEXT fused decode step reads its activations from.  Writing the
