@@ -117,6 +117,8 @@ def test_reference_grid(ext, fmt):
 DECODE_SHAPES = [  # (M, N, K)
     (16, 1, 2048), (48, 1, 4096), (100, 3, 4096), (1, 1, 2048), (17, 8, 2048), (250, 16, 4096),
     (64, 9, 6144), (333, 5, 2048), (2048, 2, 4096), (40, 16, 14336), (24, 12, 8192),
+    # activations too large for one CTA: cluster split-K (odd O, few tiles, many tiles) and the K-sliced last resort
+    (100, 8, 14336), (16, 16, 4096), (2500, 16, 4096), (33, 16, 28672),
 ]
 
 
