@@ -3,8 +3,9 @@
 
     quantize_to_q8_0 / dequantize_q8_0      utils/quantize/q8_0.py:4-100
     quantize_to_q8_1                        utils/quantize/q8_1.py:18-70
-    dequantize_q4_k                         utils/quantize/q4_k.py:146-158
-    dequantize_q6_k (fp32, like the ref)    utils/quantize/q6_k.py:138-159
+    quantize_to_q4_k / dequantize_q4_k      utils/quantize/q4_k.py:86-90, 146-158 (+ q4_k_ref.c:188-368)
+    quantize_to_q6_k / dequantize_q6_k      utils/quantize/q6_k.py:99-110, 138-159 (+ q6_k_ref.c:153-340; fp32 dequant)
 
-The K-quant *packers* (quantize_to_q4_k / q6_k, GGML's iterative search) are not provided here.
+The packers are byte-identical to the reference's (the K-quant ones reproduce GGML's iterative scale search one
+thread per sub-block, csrc/kquant_pack.cuh).
 """

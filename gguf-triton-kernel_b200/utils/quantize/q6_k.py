@@ -1,8 +1,8 @@
-"""GPU mirror of the reference's utils/quantize/q6_k.py dequantizer: returns float32 like the reference (:157)."""
+"""GPU mirrors of the reference's utils/quantize/q6_k.py: dequantizer (float32 like the reference, :157) and packer."""
 import torch
 
 from kernels import _ext
-from ._common import _lib
+from ._common import _lib, quantize_k
 
 
 def dequantize_q6_k(quantized_tensor: torch.Tensor, original_shape) -> torch.Tensor:
@@ -18,3 +18,9 @@ def dequantize_q6_k(quantized_tensor: torch.Tensor, original_shape) -> torch.Ten
         rc = _lib().ggq_dequant_q6_k_f32(q.data_ptr(), out.data_ptr(), 1, out.numel(), torch.cuda.current_stream().cuda_stream)
     _ext.check(rc, "ggq_dequant_q6_k_f32")
     return out.reshape(original_shape)
+
+
+def quantize_to_q6_k(input_tensor: torch.Tensor) -> torch.Tensor:
+    """GPU packer, byte-identical to the reference's compiled `quantize_row_q6_K_ref` behind
+    utils/quantize/q6_k.py:99-110: flat int8 [n/256 * 210] on the input's device."""
+    return quantize_k("ggq_quantize_q6_k_f32", 210, input_tensor)

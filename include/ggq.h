@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 103 /* 0.1.3 */
+#define GGQ_VERSION 104 /* 0.1.4 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -140,6 +140,13 @@ int ggq_dequant_q6_k_f16(const void* W, void* out, int64_t O, int64_t K, void* s
  * n must be a multiple of 32 (the reference raises ValueError, q8_0.py:14-15).
  */
 int ggq_quantize_q8_0_f16(const void* x, void* out, int64_t n, void* stream);
+/*
+ * K-quant packers: fp32 x[n] (16-byte aligned, n a multiple of 256) -> Q4_K blocks (n/256 * 144 B) / Q6_K blocks
+ * (n/256 * 210 B), byte-identical to the reference's compiled packers utils/quantize/q4_k_ref.c:281-368
+ * quantize_row_q4_K_ref and q6_k_ref.c:251-340 quantize_row_q6_K_ref (same fp32 operation sequence, no FMA).
+ */
+int ggq_quantize_q4_k_f32(const void* x, void* out, int64_t n, void* stream);
+int ggq_quantize_q6_k_f32(const void* x, void* out, int64_t n, void* stream);
 int ggq_quantize_q8_1_f16(const void* x, void* out, int64_t n, void* stream);
 int ggq_dequant_q6_k_f32(const void* W, void* out, int64_t O, int64_t K, void* stream);
 

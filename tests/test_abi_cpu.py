@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_queries():
     from kernels import _ext
     L = _ext.lib()
-    assert L.ggq_version() == 103
+    assert L.ggq_version() == 104
     assert L.ggq_packed_nbytes(0, 4096, 4096) == 17825792          # BASELINE config 1
     assert L.ggq_packed_nbytes(1, 128256, 4096) == 295501824       # config 2
     assert L.ggq_packed_nbytes(2, 4096, 14336) == 48168960         # config 3

@@ -78,3 +78,61 @@ def test_reference_arithmetic_mode_is_bit_identical(golden, fmt):
     got = fn(torch.from_numpy(A).cuda(), Bq, M, N, K).cpu().numpy()
     want = np.ascontiguousarray(orc.mmq_cpu(fmt, A, X, M, N, K))
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+
+
+def _kq_cases():
+    rng = np.random.default_rng(1)
+    n = 256 * 512
+    return {
+        "randn": rng.standard_normal(n).astype(np.float32),
+        "uniform positive": rng.uniform(0, 3, n).astype(np.float32),
+        "tiny": (rng.standard_normal(n) * 1e-20).astype(np.float32),
+        "large": (rng.standard_normal(n) * 3e4).astype(np.float32),
+        "zeros and constants": np.concatenate([np.zeros(512), np.full(512, 0.37), np.full(512, -1.5)]).astype(np.float32),
+        "sparse": np.where(rng.random(n) < 0.1, rng.standard_normal(n), 0).astype(np.float32),
+        "mixed scales": (rng.standard_normal(n) * np.repeat(10.0 ** rng.uniform(-6, 3, n // 32), 32)).astype(np.float32),
+    }
+
+
+@pytest.mark.parametrize("name", list(_kq_cases()))
+def test_kquant_packers_byte_identical_to_reference_library(name):
+    """GPU Q4_K / Q6_K packers vs the reference's compiled packers (oracle/_ref travels with the repo) on raw fp32."""
+    import ctypes
+    import os
+    from utils.quantize.q4_k import quantize_to_q4_k
+    from utils.quantize.q6_k import quantize_to_q6_k
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    x = _kq_cases()[name]
+    xd = torch.from_numpy(x).cuda()
+    for fn, lib, sym, blk in ((quantize_to_q4_k, "libq4_k_ref.so", "quantize_row_q4_K_ref", 144),
+                              (quantize_to_q6_k, "libq6_k_ref.so", "quantize_row_q6_K_ref", 210)):
+        ref = np.zeros(x.size // 256 * blk, dtype=np.uint8)
+        getattr(ctypes.CDLL(os.path.join(ref_dir, lib)), sym)(x.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p),
+                                                              ctypes.c_longlong(x.size))
+        got = fn(xd).cpu().numpy().view(np.uint8)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (name, sym, int((got != ref).sum()))
+
+
+def test_kquant_packers_reproduce_the_golden_fixtures(golden):
+    """fp16 weights of the golden cases -> exactly the packed bytes the reference produced for them."""
+    from utils.quantize.q4_k import quantize_to_q4_k
+    from utils.quantize.q6_k import quantize_to_q6_k
+    for fmt, fn in (("q4_k", quantize_to_q4_k), ("q6_k", quantize_to_q6_k)):
+        for c in golden[fmt]:
+            assert np.array_equal(fn(torch.from_numpy(c["W"]).cuda()).cpu().numpy(), c["A"]), (fmt, c["M"], c["K"])
+    with pytest.raises(ValueError):
+        quantize_to_q4_k(torch.zeros(100, dtype=torch.float16, device="cuda"))
+
+
+def test_packed_on_gpu_then_multiplied():
+    """pack on the GPU -> mmq on the GPU: the whole synthetic pipeline of the reference's tests without the host."""
+    from kernels.mmq_q4_k import mmq_q4_k
+    from utils.quantize.q4_k import dequantize_q4_k, quantize_to_q4_k
+    O, K, T = 512, 2048, 3
+    W = torch.randn((O, K), device="cuda", dtype=torch.float16)
+    X = torch.randn((T, K), device="cuda", dtype=torch.float16)
+    A = quantize_to_q4_k(W)
+    C = mmq_q4_k(A, X, O, T, K)
+    ref = X.float() @ dequantize_q4_k(A, (O, K)).float().t()
+    err = (C.float() - ref).norm() / ref.norm()
+    assert err < 2e-3, float(err)
