@@ -16,9 +16,13 @@
 // multiplies exactly; the power of two is folded into the fp32 scale.  (The classic 0x6400 "1024 + n"
 // magic is avoided on purpose: its bias has to be cancelled in fp32 afterwards, which costs ~10 bits of
 // the accumulator — 8e-6 vs 2e-7 relative error in the host emulator — while the subnormal form keeps
-// the addends at the magnitude of the signal.)  Products are exact and accumulate in fp32.  Because the K order inside an MMA is free as long as A and B
-// agree, lane t of a quad always takes the 4 weights that share one 32-bit word and the 4 matching
-// consecutive activations.
+// the addends at the magnitude of the signal.)  Products are exact and accumulate in fp32.  Because the K order
+// inside an MMA is free as long as A and B agree, lane t of a quad always takes the 4 weights that share one 32-bit
+// word and the 4 matching consecutive activations.
+//
+// Two tile codes per format: the general one (T = 2..16: the 8 MMA columns are 8 tokens, NT = 1 or 2 n-tiles) and the
+// single-token GEMV one (`*_gv`: the 8 columns are 8 SUB-BLOCKS of the one token, see the notes above
+// compute_q4_k_gv_impl), selected by the `GV` template flag of Tile<>.
 //
 // This header is also compiled for the host (tests/host/emu_decode.cpp) where a 32-thread warp
 // emulator supplies mma/syncwarp, so the bit manipulation is verified against the oracle without a GPU.
