@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary of libggq.so (include/ggq.h): validation + family dispatch.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/ggq.h"
 #include "common.cuh"
@@ -38,6 +39,16 @@ static int validate(int fmt, const void* W, const void* X, void* const* C_out, i
 
 static int select_family(int fmt, const MmArgs& a) {
     if (a.O < 16) return GGQ_FAMILY_GENERIC;  // less than one 16-row MMA tile: one warp per row is the better fit
+    // skinny (tcgen05, weights as the TMEM A operand): every 17 <= T <= 127, and the T <= 16 shapes where it measured
+    // faster than the mma.sync decode kernel on B200 (profiles/README.md): its cost per weight does not grow with T, the
+    // decode kernel's does (one more n-tile from T = 9, shared-memory re-reads of the activations from T = 5).  Small
+    // layers stay with the decode kernel (lower fixed cost per launch).
+    static const bool no_skinny = [] { const char* e = getenv("GGQ_SKINNY"); return e && e[0] == '0'; }();
+    if (a.T >= 2 && a.T <= 127 && !no_skinny && skinny_supports(fmt, a)) {
+        static const int thr[3] = {6, 9, 17};   // Q8_0, Q4_K, Q6_K: smallest T that goes to the skinny kernel
+        const bool big = a.O * a.K >= (int64_t{48} << 20);
+        if (a.T > 16 || (big && a.T >= thr[fmt]) || !decode_supports(fmt, a)) return GGQ_FAMILY_SKINNY;
+    }
     if (a.T <= 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;
     if (a.T >= 64 && prefill_supports(fmt, a)) return GGQ_FAMILY_PREFILL;
     if (a.T > 16 && decode_supports(fmt, a)) return GGQ_FAMILY_DECODE;  // looped over 16-token groups
@@ -82,6 +93,7 @@ static int mm(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
         case GGQ_FAMILY_GENERIC: return launch_generic(fmt, a);
         case GGQ_FAMILY_DECODE: return decode_supports(fmt, a) ? launch_decode(fmt, a) : GGQ_E_FAMILY;
         case GGQ_FAMILY_PREFILL: return prefill_supports(fmt, a) ? launch_prefill(fmt, a) : GGQ_E_FAMILY;
+        case GGQ_FAMILY_SKINNY: return skinny_supports(fmt, a) ? launch_skinny(fmt, a) : GGQ_E_FAMILY;
     }
     return GGQ_E_FAMILY;
 }
@@ -114,7 +126,7 @@ int ggq_mm_q6_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T,
 
 int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc, int64_t O,
               int64_t T, int64_t K, int family, void* stream) {
-    if (family < GGQ_FAMILY_AUTO || family > GGQ_FAMILY_PREFILL) return GGQ_E_FAMILY;
+    if (family < GGQ_FAMILY_AUTO || family > GGQ_FAMILY_SKINNY) return GGQ_E_FAMILY;
     return mm(fmt, W, X, ldx, C_out, n_out, ldc, O, T, K, family, stream);
 }
 

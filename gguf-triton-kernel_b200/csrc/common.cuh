@@ -53,8 +53,10 @@ int num_sms();  // SM count of the current device (cached per device)
 int launch_generic(int fmt, const MmArgs& a);
 int launch_decode(int fmt, const MmArgs& a);
 int launch_prefill(int fmt, const MmArgs& a);
+int launch_skinny(int fmt, const MmArgs& a);
 bool decode_supports(int fmt, const MmArgs& a);
 bool prefill_supports(int fmt, const MmArgs& a);
+bool skinny_supports(int fmt, const MmArgs& a);
 int decode_plan(int fmt, const MmArgs& a, int* out9);
 
 int launch_dequant(int fmt, const uint8_t* W, void* out, int64_t O, int64_t K, cudaStream_t s);

@@ -1,22 +1,21 @@
 // prefill.cu — tensor-bound family: C[T, O] = X[T, K] . dequant(W)[O, K]^T for large T on tcgen05.
 //
-// One CTA computes a 256-token x 256-out-feature tile (two 128x256 fp32 accumulators = all 512 TMEM
-// columns), so every dequantized weight is reused by 256 tokens.  Warp roles (10 warps):
+// A CTA PAIR (cta_group::2, cluster of 2) computes a 512-token x 256-out-feature tile: two M256 N256 fp32
+// accumulators fill all 512 TMEM columns of both SMs, so every dequantized weight is reused by 512 tokens.
+// Warp roles per CTA (10 warps):
 //
-//   warp 0      TMA producer   X tiles [2 x 128 tokens, 64 k] (2-D tensor map, SWIZZLE_128B) and packed
-//                              weight "units" [128 rows, one block column] (2-D tensor map over the raw
+//   warp 0      TMA producer   X tiles [2 x 128 tokens, 64 k] (2-D tensor map, SWIZZLE_128B, .cta_group::2) and
+//                              packed weight "units" [128 rows, one block column] (2-D tensor map over the raw
 //                              GGUF bytes viewed as int32 — rows are copied verbatim, no repacking)
-//   warp 1      MMA issuer     one elected thread: 8 x tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
-//                              per 64-k stage, A and B from shared memory, D in TMEM; tcgen05.commit
-//                              releases the stage and finally publishes the accumulators
-//   warps 2..9  dequant        256 threads = 256 weight rows: packed unit row -> 64 bit-exact fp16 weights
-//                              (prefill_tile.cuh) -> K-major SWIZZLE_128B B tile (hand-swizzled 16-byte
-//                              stores + fence.proxy.async), then the same warps run the epilogue:
-//                              tcgen05.ld 32x32b.x32 -> fp16 -> global
+//   warp 1      MMA issuer     leader CTA only, one elected thread: tcgen05.mma.cta_group::2.kind::f16
+//                              (M256 N256 K16), A and B from shared memory, D in TMEM; tcgen05.commit releases
+//                              the stage in both CTAs and finally publishes the accumulators
+//   warps 2..9  dequant        two ping-pong groups of 128 threads = the CTA's 128 weight rows: packed unit row ->
+//                              64 bit-exact fp16 weights (prefill_tile.cuh) -> K-major SWIZZLE_128B B tile
+//                              (hand-swizzled 16-byte stores + fence.proxy.async), then the same warps run the
+//                              epilogue: tcgen05.ld 32x32b.x32 -> fp16 -> global
 //
-// mbarrier pipelines: x_full[s] (TMA tx) / b_full[s] (8 dequant warps) -> MMA -> free[s] (tcgen05.commit);
-// w_full[u] (TMA tx) -> dequant -> w_empty[u] (4 warps); acc_full (tcgen05.commit) -> epilogue.
-// Roofline: 2*T*O*K FLOP on the fp16 tensor pipe; packed weights are read T/256 times (L2-resident
+// Roofline: 2*T*O*K FLOP on the fp16 tensor pipe; packed weights are read T/512 times (L2-resident
 // across the token tiles that run concurrently), X is read O/256 times.
 #include <algorithm>
 #include <cstdlib>
@@ -27,255 +26,20 @@
 #include "prefill_tile.cuh"
 #include "ptx.cuh"
 #include "tma.cuh"
+#include "umma.cuh"
 
 namespace ggq {
 namespace pre {
 
-constexpr int BM = 256;          // tokens per CTA tile (2 x UMMA M=128)
-constexpr int BN = 256;          // out-features per CTA tile (UMMA N)
 constexpr int BK = 64;           // k per pipeline stage: one 128-byte swizzle atom of fp16
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2;  // 32 KB: two [128 x 64] fp16 sub-tiles
-constexpr int B_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int UNIT_ROWS = 128;
-constexpr int NUM_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2..9 dequant/epilogue
+constexpr int UNIT_ROWS = 128;   // rows of a packed staging unit (one TMA box)
 constexpr int DQ_WARPS = 8;
-
-template <int FMT> struct Ring {  // packed staging units in flight (2 row halves per block column)
-    static constexpr int DEPTH = FMT == 2 ? 3 : 4;
-    static constexpr int UNIT_BYTES = UNIT_ROWS * Unit<FMT>::BOX_BYTES;
-    static constexpr int KB_PER_UNIT = Unit<FMT>::UNIT_K / BK;  // 64-k stages served by one unit
-};
-
-template <int FMT> constexpr int smem_bytes() {
-    return 1024 /*align slack*/ + STAGES * STAGE_BYTES + Ring<FMT>::DEPTH * Ring<FMT>::UNIT_BYTES + 256 /*barriers*/;
-}
-
-// ---- tcgen05 / TMA wrappers -------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start address >> 4 | LBO (unused for swizzled K-major, 1) << 16 | SBO = 1024 B (8 rows x 128 B) >> 4 << 32 |
-// version 1 << 46 | layout SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
-    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (uint64_t{1} << 16) | (uint64_t{1024 >> 4} << 32) |
-           (uint64_t{1} << 46) | (uint64_t{2} << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), both K-major,
-// N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 
 struct Params {
     OutPtrs outs;
     int64_t ldc, O, T;
     int K;
 };
-
-template <int FMT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-prefill_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
-    using U = Unit<FMT>;
-    using R = Ring<FMT>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t{1023});
-    uint8_t* stages = smem;                                   // [STAGES][A | B], 1024-byte aligned tiles
-    uint8_t* units = smem + STAGES * STAGE_BYTES;             // [DEPTH][128 rows][BOX_BYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(units + R::DEPTH * R::UNIT_BYTES);
-    uint64_t* x_full = bars;                 // [STAGES]
-    uint64_t* b_full = bars + STAGES;        // [STAGES]
-    uint64_t* free_ = bars + 2 * STAGES;     // [STAGES]
-    uint64_t* w_full = bars + 3 * STAGES;    // [DEPTH]
-    uint64_t* w_empty = w_full + R::DEPTH;   // [DEPTH]
-    uint64_t* acc_full = w_empty + R::DEPTH; // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * BM;  // token tile (fastest: co-resident CTAs share weight tiles in L2)
-    const int64_t o0 = static_cast<int64_t>(blockIdx.y) * BN;  // out-feature tile
-    const int num_kb = p.K / BK;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&x_full[s], 1);
-            mbar_init(&b_full[s], DQ_WARPS);
-            mbar_init(&free_[s], 1);
-        }
-        for (int u = 0; u < R::DEPTH; ++u) {
-            mbar_init(&w_full[u], 1);
-            mbar_init(&w_empty[u], DQ_WARPS / 2);
-        }
-        mbar_init(acc_full, 1);
-        fence_mbar_init();
-        prefetch_tmap(&map_x);
-        prefetch_tmap(&map_w);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int uidx = 0;  // running unit counter (ring position = uidx % DEPTH)
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if (kb % R::KB_PER_UNIT == 0) {
-                    const int col = kb / R::KB_PER_UNIT;                       // block column
-                    const int byte0 = (col * U::UNIT_BYTES) & ~15;            // 16-byte aligned superset start
-                    for (int half = 0; half < 2; ++half, ++uidx) {
-                        const int slot = uidx % R::DEPTH;
-                        const uint32_t use = static_cast<uint32_t>(uidx / R::DEPTH);
-                        if (use > 0) mbar_wait(&w_empty[slot], (use - 1) & 1u);
-                        mbar_arrive_expect_tx(&w_full[slot], R::UNIT_BYTES);
-                        tma_load_2d(units + slot * R::UNIT_BYTES, &map_w, byte0 / 4,
-                                    static_cast<int>(o0) + half * UNIT_ROWS, &w_full[slot]);
-                    }
-                }
-                const int s = kb % STAGES;
-                const uint32_t use = static_cast<uint32_t>(kb / STAGES);
-                if (use > 0) mbar_wait(&free_[s], (use - 1) & 1u);
-                mbar_arrive_expect_tx(&x_full[s], A_BYTES);
-                uint8_t* a = stages + s * STAGE_BYTES;
-                tma_load_2d(a, &map_x, kb * BK, static_cast<int>(t0), &x_full[s]);
-                tma_load_2d(a + A_BYTES / 2, &map_x, kb * BK, static_cast<int>(t0) + 128, &x_full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = static_cast<uint32_t>(kb / STAGES) & 1u;
-                mbar_wait(&x_full[s], ph);
-                mbar_wait(&b_full[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(stages + s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = smem_desc_sw128(a_addr + t * (A_BYTES / 2) + k * 32);
-                        const uint64_t bd = smem_desc_sw128(b_addr + k * 32);
-                        umma_f16(tmem_base + t * BN, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
-                    }
-                }
-                umma_commit(&free_[s]);  // stage reusable once these MMAs have read it
-            }
-            umma_commit(acc_full);
-        }
-    } else {
-        // ================= dequant warps (then epilogue) =================
-        const int dq = threadIdx.x - 64;        // 0..255 = weight row inside the tile
-        const int dwarp = warp - 2;             // 0..7
-        const int half = dq >> 7;               // which 128-row unit
-        const int urow = dq & 127;
-        const uint32_t sw = static_cast<uint32_t>(dq & 7);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int col = kb / R::KB_PER_UNIT, kin = kb % R::KB_PER_UNIT;
-            const int uidx = 2 * col + half;
-            const int slot = uidx % R::DEPTH;
-            if (kin == 0) mbar_wait(&w_full[slot], static_cast<uint32_t>(uidx / R::DEPTH) & 1u);
-            const int s = kb % STAGES;
-            const uint32_t use = static_cast<uint32_t>(kb / STAGES);
-            if (use > 0) mbar_wait(&free_[s], (use - 1) & 1u);
-            uint4 v[8];
-            const int off = (col * U::UNIT_BYTES) & 15;
-            dequant64(U{}, units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
-            uint8_t* brow = stages + s * STAGE_BYTES + A_BYTES + (dq >> 3) * 1024 + (dq & 7) * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(j) ^ sw) << 4)) = v[j];
-            fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&b_full[s]);
-                if (kin == R::KB_PER_UNIT - 1) mbar_arrive(&w_empty[slot]);
-            }
-        }
-        // ---- epilogue: TMEM -> registers -> fp16 -> global ----
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int chalf = dwarp >> 2;           // which 128 columns of the 256
-        const bool vec_ok = (p.ldc % 8 == 0);
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-            const int64_t tok = t0 + t * 128 + q * 32 + lane;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                const int col0 = chalf * 128 + cc * 32;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(t * BN + col0), r);
-                tmem_ld_wait();
-                if (tok < p.T) {
-                    uint32_t h[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) h[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                    const int64_t oc = o0 + col0;
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        if (o >= p.outs.n) break;
-                        __half* dst = p.outs.p[o] + tok * p.ldc + oc;
-                        if (vec_ok && oc + 32 <= p.O && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                reinterpret_cast<uint4*>(dst)[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (oc + i < p.O)
-                                    dst[i] = __ushort_as_half(static_cast<unsigned short>((h[i >> 1] >> (16 * (i & 1))) & 0xffffu));
-                        }
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
 
 // =================================================================================================
 // 2-CTA variant (cta_group::2): a CTA PAIR computes 512 tokens x 256 out-features.  Each UMMA is
@@ -568,44 +332,27 @@ static int launch_t(const MmArgs& a) {
     if (!make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_INT32, a.W, static_cast<uint64_t>(rowB / 4), static_cast<uint64_t>(a.O),
                      static_cast<uint64_t>(rowB), U::BOX_BYTES / 4, UNIT_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE))
         return static_cast<int>(cudaErrorInvalidValue);
-    static const bool one_cta = [] { const char* e = getenv("GGQ_PREFILL_1CTA"); return e && e[0] == '1'; }();
     Params p;
     p.outs = make_outs(a);
     p.ldc = a.ldc;
     p.O = a.O;
     p.T = a.T;
     p.K = static_cast<int>(a.K);
-    if (!one_cta) {
-        auto kern2 = two::prefill2_kernel<FMT>;
-        static int configured2[64] = {0};
-        int dev2 = 0;
-        cudaGetDevice(&dev2);
-        if (dev2 >= 0 && dev2 < 64 && !configured2[dev2]) {
-            cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, two::smem_bytes2<FMT>());
-            if (e != cudaSuccess) return static_cast<int>(e);
-            configured2[dev2] = 1;
-        }
-        const int pairs_t = static_cast<int>((a.T + 511) / 512);
-        const int64_t pairs_o = (a.O + 255) / 256;
-        const int64_t ctas = 2 * pairs_t * pairs_o;
-        if (ctas > 0x7fffffff) return GGQ_E_SHAPE;
-        kern2<<<static_cast<unsigned>(ctas), two::NUM_THREADS2, two::smem_bytes2<FMT>(), a.stream>>>(map_x, map_w, p, pairs_t);
-        count_launch();
-        return static_cast<int>(cudaGetLastError());
-    }
-    auto kern = prefill_kernel<FMT>;
-    static int configured[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<FMT>());
+    auto kern2 = two::prefill2_kernel<FMT>;
+    static int configured2[64] = {0};
+    int dev2 = 0;
+    cudaGetDevice(&dev2);
+    if (dev2 >= 0 && dev2 < 64 && !configured2[dev2]) {
+        cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, two::smem_bytes2<FMT>());
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured[dev] = 1;
+        configured2[dev2] = 1;
     }
-    // token tiles vary fastest, so the CTAs resident at the same time read the same packed weight tiles (L2 hits)
-    dim3 grid(static_cast<unsigned>((a.T + BM - 1) / BM), static_cast<unsigned>((a.O + BN - 1) / BN));
-    if (grid.y > 65535) return GGQ_E_SHAPE;
-    kern<<<grid, NUM_THREADS, smem_bytes<FMT>(), a.stream>>>(map_x, map_w, p);
+    // token tiles vary fastest, so the pairs resident at the same time read the same packed weight tiles (L2 hits)
+    const int pairs_t = static_cast<int>((a.T + 511) / 512);
+    const int64_t pairs_o = (a.O + 255) / 256;
+    const int64_t ctas = 2 * pairs_t * pairs_o;
+    if (ctas > 0x7fffffff) return GGQ_E_SHAPE;
+    kern2<<<static_cast<unsigned>(ctas), two::NUM_THREADS2, two::smem_bytes2<FMT>(), a.stream>>>(map_x, map_w, p, pairs_t);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

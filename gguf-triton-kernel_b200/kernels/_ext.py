@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(_PKG, "libggq.so")
 _lib = None
 
 GGQ_Q8_0, GGQ_Q4_K, GGQ_Q6_K = 0, 1, 2
-FAMILY_AUTO, FAMILY_GENERIC, FAMILY_DECODE, FAMILY_PREFILL = 0, 1, 2, 3
+FAMILY_AUTO, FAMILY_GENERIC, FAMILY_DECODE, FAMILY_PREFILL, FAMILY_SKINNY = 0, 1, 2, 3, 4
 FMT_ID = {"q8_0": GGQ_Q8_0, "q4_k": GGQ_Q4_K, "q6_k": GGQ_Q6_K}
 FMT_QK = {GGQ_Q8_0: 32, GGQ_Q4_K: 256, GGQ_Q6_K: 256}
 FMT_BLK = {GGQ_Q8_0: 34, GGQ_Q4_K: 144, GGQ_Q6_K: 210}

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 104 /* 0.1.4 */
+#define GGQ_VERSION 105 /* 0.1.5 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -47,11 +47,13 @@ extern "C" {
 #define GGQ_Q6_K 2 /* 256 weights / 210 B: ql[128], qh[64], int8 scales[16], fp16 d                 */
 
 /* kernel families (ggq_mm_ex `family`) */
-#define GGQ_FAMILY_AUTO    0 /* decode for T<=16 (when the shape is aligned), prefill for large T   */
+#define GGQ_FAMILY_AUTO    0 /* decode / skinny for T<=16, skinny for 17..127, prefill from 128 on   */
 #define GGQ_FAMILY_GENERIC 1 /* any shape, any alignment; one warp per output row                    */
 #define GGQ_FAMILY_DECODE  2 /* HBM-bound skinny GEMM, T<=16: TMA bulk-staged packed rows,           */
                              /* register unpack, mma.sync m16n8k16 f16->f32                           */
 #define GGQ_FAMILY_PREFILL 3 /* tensor-bound GEMM: packed tiles -> smem dequant -> tcgen05.mma/TMEM   */
+#define GGQ_FAMILY_SKINNY  4 /* HBM-bound skinny GEMM, 2<=T<=128: packed tiles -> register dequant ->  */
+                             /* tcgen05.st (weights = TMEM A operand) -> tcgen05.mma, N = tokens      */
 
 /*
  * mmq entry points.  Replace the bodies of

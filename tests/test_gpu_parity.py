@@ -259,9 +259,88 @@ def test_full_size_properties(ext, fmt):
     check_tier1(fmt, Asub, X1, len(rows), 4, K, C1[:, rows].cpu().numpy().astype(np.float16), "full-size sample")
 
 
+# ---- skinny family (tcgen05, weights dequantized into the TMEM A operand): 2 <= T <= 128 ----------------
+SKINNY_SHAPES = [  # (M = out-features, N = tokens, K)
+    (128, 2, 256), (128, 16, 1024), (100, 3, 4096), (1000, 8, 2048), (129, 16, 4096), (4096, 16, 4096), (2500, 5, 4096),
+    (333, 32, 2048), (777, 64, 4096), (515, 100, 2048), (300, 127, 2048), (16, 4, 2048), (5000, 7, 256), (9000, 30, 2304),
+    (3000, 16, 16384), (20000, 16, 2048), (640, 128, 2048), (257, 17, 6144),
+]
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("shape", SKINNY_SHAPES)
+def test_skinny_family(ext, fmt, shape):
+    M, N, K = shape
+    if fmt == "q6_k":
+        K = max(2048, K // 2048 * 2048)  # rows must be whole 16-byte vectors: K % 2048 == 0
+    A = orc.random_blocks(fmt, M, K, seed=M + N)
+    X = rand_x(N, K, K + 2)
+    if M * K > 2 ** 24:  # big layers: the oracle on sampled rows (first / last tile + random), rows are independent
+        rng = np.random.default_rng(5)
+        rows = np.unique(np.concatenate([np.arange(128), np.arange(M - 128, M), rng.choice(M, 256, replace=False)]))
+        C = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_SKINNY)
+        rowB = orc.packed_nbytes(fmt, 1, K)
+        Asub = np.concatenate([A[r * rowB:(r + 1) * rowB] for r in rows])
+        check_tier1(fmt, Asub, X, len(rows), N, K, C[:, rows], "skinny sampled")
+        return
+    C = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_SKINNY)
+    check_tier1(fmt, A, X, M, N, K, C, "skinny")
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_skinny_repeated_launches_are_deterministic(ext, fmt):
+    """Tiles cut by a CTA range boundary are combined through a workspace + flags that the finishing CTA re-arms:
+    back-to-back launches (dependent launch overlap, rotating workspaces) and CUDA-graph replays must be bit-identical."""
+    M, N, K = 4096, 16, 4096   # 32 row tiles over 148 CTAs: almost every tile is cut
+    f = ext.FMT_ID[fmt]
+    Ad = dev(orc.random_blocks(fmt, M, K, seed=3))
+    Xd = dev(rand_x(N, K, 4))
+    first = ext.mm(f, Ad, Xd, M, N, K, family=ext.FAMILY_SKINNY)
+    torch.cuda.synchronize()
+    outs = [ext.mm(f, Ad, Xd, M, N, K, family=ext.FAMILY_SKINNY) for _ in range(9)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(first, o) for o in outs)
+    bufs = [torch.empty_like(first) for _ in range(6)]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for b in bufs:
+            ext.mm(f, Ad, Xd, M, N, K, family=ext.FAMILY_SKINNY, out=b)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(first, b) for b in bufs)
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_skinny_matches_decode_and_prefill(ext, fmt):
+    """Three independent implementations of the same product (mma.sync decode, tcgen05 prefill, tcgen05 skinny)."""
+    M, N, K = 512, 16, 2048
+    A = orc.random_blocks(fmt, M, K, seed=41)
+    X = rand_x(N, K, 42)
+    Cs = run_mm(ext, fmt, A, X, M, N, K, family=ext.FAMILY_SKINNY).astype(np.float32)
+    for fam in (ext.FAMILY_DECODE, ext.FAMILY_PREFILL):
+        Co = run_mm(ext, fmt, A, X, M, N, K, family=fam).astype(np.float32)
+        mx, fro = orc.tier1_errors(Cs, Co)
+        assert fro < 1.5e-3 and mx < 5e-3, (fam, mx, fro)
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+def test_tokens_17_to_127_take_the_skinny_family(ext, fmt):
+    """T = 17 .. 127 (between the decode and prefill tile sizes) is one pass of the skinny kernel."""
+    M, K = 1024, 2048
+    A = orc.random_blocks(fmt, M, K, seed=51)
+    for N in (17, 31, 48, 65, 100, 127):
+        assert ext.lib().ggq_select_family(ext.FMT_ID[fmt], M, N, K) == ext.FAMILY_SKINNY
+        X = rand_x(N, K, N)
+        l0 = ext.launch_count()
+        C = run_mm(ext, fmt, A, X, M, N, K)
+        assert ext.launch_count() - l0 == 1
+        check_tier1(fmt, A, X, M, N, K, C, f"auto T={N}")
+
+
 # ---- extended C-ABI form: strides, several outputs, fused-exchange entry point on one rank ---------
 @pytest.mark.parametrize("fmt", FMTS)
-@pytest.mark.parametrize("family,N", [(1, 5), (2, 7), (3, 96)])
+@pytest.mark.parametrize("family,N", [(1, 5), (2, 7), (3, 96), (4, 11), (4, 70)])
 def test_mm_ex_strides_and_multiple_outputs(ext, fmt, family, N):
     M, K = 80, 2048
     ldx, ldc = K + 64, M + 24
