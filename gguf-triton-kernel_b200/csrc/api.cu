@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary of libggq.so (include/ggq.h): validation + family dispatch.
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 
 #include "../../include/ggq.h"
@@ -224,6 +225,42 @@ int ggq_decode_plan(int fmt, int64_t O, int64_t T, int64_t K, int* out9) {
     a.K = K;
     if (!decode_supports(fmt, a)) return GGQ_E_FAMILY;
     return decode_plan(fmt, a, out9);
+}
+
+int ggq_describe(int fmt, int64_t O, int64_t T, int64_t K, char* out, int cap) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 1 || T < 1 || K < fmt_qk(fmt) || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    if (!out || cap < 1) return GGQ_E_POINTER;
+    MmArgs a{};
+    a.W = reinterpret_cast<const uint8_t*>(uintptr_t{256});
+    a.X = reinterpret_cast<const void*>(uintptr_t{256});
+    a.n_out = 1;
+    a.ldx = K;
+    a.ldc = O;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    static const char* const names[3] = {"Q8_0", "Q4_K", "Q6_K"};
+    switch (select_family(fmt, a)) {
+        case GGQ_FAMILY_GENERIC:
+            snprintf(out, cap, "ggq::gen::generic_kernel<%s> (one warp per output row)", names[fmt]);
+            return 0;
+        case GGQ_FAMILY_SKINNY: skinny_describe(fmt, a, out, cap); return 0;
+        case GGQ_FAMILY_PREFILL:
+            snprintf(out, cap, "ggq::pre::two::prefill2_kernel<%s> (tcgen05.mma cta_group::2, 512 x 256 tiles)", names[fmt]);
+            return 0;
+        case GGQ_FAMILY_DECODE: {
+            int v[9];
+            if (decode_plan(fmt, a, v) != 0) return GGQ_E_FAMILY;
+            const int tt = static_cast<int>(T > 16 ? 16 : T);
+            const bool gv = tt == 1 && v[1] == 1 && v[3] == 1;
+            snprintf(out, cap, "ggq::dec::decode_kernel<%s,NT=%d,AT=%d,%s> grid=%d occ=%d stages=%d k-slices=%d%s", names[fmt], v[2],
+                     v[1], gv ? "GV=1 (single-token GEMV tile code)" : "GV=0", v[6] / 100, v[6] % 100, v[5], v[3],
+                     T > 16 ? " (16-token passes)" : "");
+            return 0;
+        }
+    }
+    return GGQ_E_FAMILY;
 }
 
 int64_t ggq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

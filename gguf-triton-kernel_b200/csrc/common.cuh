@@ -58,6 +58,7 @@ bool decode_supports(int fmt, const MmArgs& a);
 bool prefill_supports(int fmt, const MmArgs& a);
 bool skinny_supports(int fmt, const MmArgs& a);
 int decode_plan(int fmt, const MmArgs& a, int* out9);
+int skinny_describe(int fmt, const MmArgs& a, char* out, int cap);
 
 int launch_dequant(int fmt, const uint8_t* W, void* out, int64_t O, int64_t K, cudaStream_t s);
 // vectorized dequantize built on the prefill family's dequant64(); returns 0 if the shape is not eligible

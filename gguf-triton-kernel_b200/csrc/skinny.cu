@@ -634,6 +634,21 @@ bool skinny_supports(int fmt, const MmArgs& a) {
     return a.sync == nullptr;
 }
 
+// "skinny_kernel<FMT, N, WU, G, MAXT>" of the launch launch_skinny() would make (bench.py / ggq_describe)
+int skinny_describe(int fmt, const MmArgs& a, char* out, int cap) {
+    const int unit_k = fmt == GGQ_Q8_0 ? 128 : 256;
+    const int units = static_cast<int>(a.K / unit_k);
+    const bool two = units % 2 == 0;
+    int N, WU, G, MAXT;
+    if (a.T <= 16) { N = 16; WU = two ? 2 : 1; G = 3; MAXT = 4; }
+    else if (a.T <= 32) { N = 32; WU = two ? 2 : 1; G = 3; MAXT = 2; }
+    else if (a.T <= 64) { N = 64; WU = 1; G = 3; MAXT = 1; }
+    else { N = 128; WU = 1; G = 2; MAXT = 1; }
+    static const char* const names[3] = {"Q8_0", "Q4_K", "Q6_K"};
+    return snprintf(out, cap, "ggq::skn::skinny_kernel<%s,N=%d,WU=%d,G=%d,MAXT=%d> (tcgen05.mma, weights in TMEM)", names[fmt],
+                    N, WU, G, MAXT);
+}
+
 int launch_skinny(int fmt, const MmArgs& a) {
     switch (fmt) {
         case GGQ_Q8_0: return skn::launch_fmt<0>(a);

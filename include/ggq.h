@@ -171,6 +171,10 @@ int ggq_select_family(int fmt, int64_t O, int64_t T, int64_t K);
  * stages per warp, CTAs, batches, dynamic shared memory bytes}.  0, or GGQ_E_* (<0). */
 int ggq_decode_plan(int fmt, int64_t O, int64_t T, int64_t K, int* out9);
 
+/* Host-only: one-line description (kernel template + plan) of the launch GGQ_FAMILY_AUTO makes for this problem,
+ * written to out[cap] (NUL-terminated).  0, or GGQ_E_* (<0).  bench.py reports it as `roofline.kernel`. */
+int ggq_describe(int fmt, int64_t O, int64_t T, int64_t K, char* out, int cap);
+
 /* Kernels launched by this library since load (all families; for bench.py's `gpu_launches`). */
 int64_t ggq_launch_count(void);
 
