@@ -46,7 +46,7 @@ static int select_family(int fmt, const MmArgs& a) {
     // layers stay with the decode kernel (lower fixed cost per launch).
     static const bool no_skinny = [] { const char* e = getenv("GGQ_SKINNY"); return e && e[0] == '0'; }();
     if (a.T >= 2 && a.T <= 127 && !no_skinny && skinny_supports(fmt, a)) {
-        static const int thr[3] = {6, 9, 17};   // Q8_0, Q4_K, Q6_K: smallest T that goes to the skinny kernel
+        static const int thr[3] = {6, 9, 9};    // Q8_0, Q4_K, Q6_K: smallest T that goes to the skinny kernel
         const bool big = a.O * a.K >= (int64_t{48} << 20);
         if (a.T > 16 || (big && a.T >= thr[fmt]) || !decode_supports(fmt, a)) return GGQ_FAMILY_SKINNY;
     }
@@ -131,19 +131,32 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
     return mm(fmt, W, X, ldx, C_out, n_out, ldc, O, T, K, family, stream);
 }
 
-int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc, int64_t O,
-                int64_t T, int64_t K, const ggq_peer_sync* sync, int* ctas_out, void* stream) {
-    const int v = validate(fmt, W, X, C_out, n_out, ldx, ldc, O, T, K);
-    if (v != 0) return v;
-    if (!sync || !ctas_out || sync->world < 1 || sync->world > 8 || sync->rank < 0 || sync->rank >= sync->world ||
-        !sync->flags_local || !sync->counter)
+int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* C, int64_t ldc, int64_t O, int64_t T, int64_t K,
+                const ggq_peer_sync* sync, int* ctas_out, void* stream) {
+    if (!sync || !ctas_out || sync->world < 2 || sync->world > 8 || sync->rank < 0 || sync->rank >= sync->world ||
+        sync->x_owner < 0 || sync->x_owner >= sync->world || !sync->counter || !sync->c_land || !C)
         return GGQ_E_POINTER;
-    if (O < 16 || T < 1 || T > 16 || K < fmt_qk(fmt)) return GGQ_E_FAMILY;
+    const bool owner = sync->rank == sync->x_owner;
+    void* outs[1] = {static_cast<__half*>(C) + sync->rank * O};   // this rank's own columns
+    // the non-owners never dereference X (their activations arrive in x_land): validate() only needs a non-null pointer
+    const int v = validate(fmt, W, owner ? X : W, outs, 1, ldx, ldc, O, T, K);
+    if (v != 0) return v;
+    if (O < 16 || T < 1 || T > 8 || K < fmt_qk(fmt)) return GGQ_E_FAMILY;
+    if (O % 4 != 0 || K % 4 != 0 || T * K > 65536 || ldc < sync->world * O || ldc % 4 != 0) return GGQ_E_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(C) & 7) != 0) return GGQ_E_POINTER;
+    if (sync->c_land_half < sync->world * T * O * 4 || sync->c_land_half % 16 != 0) return GGQ_E_SHAPE;
+    if (sync->x_land_half < T * K * 4 || sync->x_land_half % 16 != 0) return GGQ_E_SHAPE;
+    for (int i = 0; i < sync->world; ++i) {
+        if (i == sync->rank) continue;
+        if (!sync->c_land_peer[i]) return GGQ_E_POINTER;
+        if (owner && !sync->x_land_peer[i]) return GGQ_E_POINTER;
+    }
+    if (!owner && !sync->x_land) return GGQ_E_POINTER;
     MmArgs a{};
     a.W = static_cast<const uint8_t*>(W);
-    a.X = X;
-    for (int i = 0; i < n_out; ++i) a.C[i] = C_out[i];
-    a.n_out = n_out;
+    a.X = owner ? X : W;
+    a.C[0] = outs[0];
+    a.n_out = 1;
     a.ldx = ldx;
     a.ldc = ldc;
     a.O = O;
@@ -151,29 +164,29 @@ int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const*
     a.K = K;
     a.stream = static_cast<cudaStream_t>(stream);
     PeerSync ps{};
-    ps.flags_local = sync->flags_local;
-    for (int i = 0; i < 8; ++i) ps.flags_peer[i] = sync->flags_peer[i];
-    ps.counter = sync->counter;
-    ps.x_ready = sync->x_ready;
-    ps.x_publish = sync->x_publish;
-    ps.epoch = sync->epoch;
-    ps.counter_target = sync->counter_base;  // the planner adds the grid size
     ps.rank = sync->rank;
     ps.world = sync->world;
+    ps.x_owner = sync->x_owner;
+    ps.epoch = sync->epoch;
+    ps.counter = sync->counter;
     ps.epoch_dev = sync->epoch_dev;
-    if (sync->epoch_dev) {  // replayable mode: kernel-maintained epoch, counter starts at 0 every call
-        if (!sync->X_alt) return GGQ_E_POINTER;
-        for (int i = 0; i < n_out; ++i)
-            if (!sync->C_alt[i]) return GGQ_E_POINTER;
-        ps.counter_target = 0;
-        ps.X_alt = static_cast<const uint8_t*>(sync->X_alt);
-        for (int i = 0; i < 8; ++i) ps.alt_out[i] = static_cast<__half*>(sync->C_alt[i < n_out ? i : 0]);
+    ps.C_full = static_cast<__half*>(C);
+    if (sync->epoch_dev) {  // replayable mode: kernel-maintained epoch, odd epochs use the alternate buffers
+        if ((owner && !sync->X_alt) || !sync->C_alt || (reinterpret_cast<uintptr_t>(sync->C_alt) & 7) != 0) return GGQ_E_POINTER;
+        ps.X_alt = static_cast<const uint8_t*>(owner ? sync->X_alt : W);
+        ps.C_alt = static_cast<__half*>(sync->C_alt);
     }
-    for (int i = 0; i < 8; ++i)
-        ps.x_push[i] = (sync->x_publish && i < sync->world && i != sync->rank) ? static_cast<uint4*>(sync->x_push[i]) : nullptr;
-    if ((ldx & 7) != 0)
-        for (int i = 0; i < 8; ++i)
-            if (ps.x_push[i]) return GGQ_E_SHAPE;  // the push copies whole 16-byte vectors
+    ps.x_land = static_cast<uint4*>(sync->x_land);
+    ps.c_land = static_cast<uint4*>(sync->c_land);
+    for (int i = 0; i < 8; ++i) {
+        const bool peer = i < sync->world && i != sync->rank;
+        ps.x_land_peer[i] = (peer && owner) ? static_cast<uint4*>(sync->x_land_peer[i]) : nullptr;
+        ps.c_land_peer[i] = peer ? static_cast<uint4*>(sync->c_land_peer[i]) : nullptr;
+    }
+    ps.x_half_lines = static_cast<uint32_t>(sync->x_land_half / 16);
+    ps.c_half_lines = static_cast<uint32_t>(sync->c_land_half / 16);
+    ps.status = sync->status;
+    ps.timeout_ns = sync->timeout_ns ? sync->timeout_ns : 2000000000ull;
     a.sync = &ps;
     a.ctas_out = ctas_out;
     if (!decode_supports(fmt, a)) return GGQ_E_FAMILY;

@@ -7,18 +7,21 @@
 namespace ggq {
 
 // In-kernel N-split exchange (see ggq_peer_sync in include/ggq.h); world == 0 means disabled.
-struct PeerSync {
-    uint32_t* flags_local;
-    uint32_t* flags_peer[8];
+struct PeerSync {            // device-side view of ggq_peer_sync (include/ggq.h)
+    int rank, world, x_owner;
+    uint32_t epoch;
     uint32_t* counter;
-    const uint32_t* x_ready;
-    uint32_t* x_publish;
-    uint32_t epoch, counter_target;
-    int rank, world;
     uint32_t* epoch_dev;      // replayable mode: epoch of a call = *epoch_dev + 1 (kernel-maintained)
     const uint8_t* X_alt;     // odd epochs read these activations ...
-    __half* alt_out[8];       // ... and store here
-    uint4* x_push[8];         // owner rank: peers' landing buffers for the activations (or null)
+    __half* C_alt;            // ... and store here (column 0 of the full row)
+    __half* C_full;           // even epochs: column 0 of the full [T, ldc] row
+    uint4* x_land;            // LL lines of the activations, two parity halves
+    uint4* x_land_peer[8];
+    uint4* c_land;            // LL lines of the peers' output slices, two parity halves
+    uint4* c_land_peer[8];
+    uint32_t x_half_lines, c_half_lines;   // 16-byte lines per parity half
+    uint32_t* status;         // first GGQ_SYNC_* code of a wait that gave up (or null)
+    unsigned long long timeout_ns;
 };
 
 struct MmArgs {

@@ -55,12 +55,50 @@ struct Params {
     int n_slices;
     int num_batches;
     int stages;
-    int bulk_push;         // fused exchange: copy the CTA's finished rows to the peers in 16-byte vectors at the end
+    int l2_prefetch_bytes; // fused exchange: bytes of the CTA's weight range prefetched into L2 before the first wait
     int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
     PeerSync sync;      // world == 0: no cross-GPU synchronisation
     uint32_t x_stride;  // bytes between token rows in shared memory
     uint32_t off_bars, off_x, off_tbl, off_ring, off_scr, off_red, off_mbox;
 };
+
+// ---- flag-in-data ("LL") lines of the fused N-split exchange: 16 bytes = {data0, epoch, data1, epoch} ---------------
+__device__ __forceinline__ void ll_store(uint4* dst, uint32_t d0, uint32_t d1, uint32_t flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(d0), "r"(flag), "r"(d1), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* src) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+    return v;
+}
+// Polls a line of this rank's landing buffer until both flag words carry `flag`.  Bounded: gives up after `timeout_ns`
+// of the global timer (or as soon as another thread has given up) and records `code` in *status.  `dead` short-cuts
+// every later wait of a thread that has given up once.
+__device__ __noinline__ uint2 ll_wait_slow(const uint4* src, uint32_t flag, const PeerSync& sy, uint32_t code, bool& dead) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i) {
+            const uint4 v = ll_load(src);
+            if (v.y == flag && v.w == flag) return make_uint2(v.x, v.z);
+        }
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const bool other = sy.status != nullptr && *reinterpret_cast<volatile const uint32_t*>(sy.status) != 0u;
+        if (other || t - t0 > sy.timeout_ns) {
+            if (sy.status != nullptr) atomicCAS(sy.status, 0u, code);
+            dead = true;
+            return make_uint2(0u, 0u);
+        }
+    }
+}
+__device__ __forceinline__ uint2 ll_wait(const uint4* src, uint32_t flag, const PeerSync& sy, uint32_t code, bool& dead) {
+    if (dead) return make_uint2(0u, 0u);
+    const uint4 v = ll_load(src);
+    if (v.y == flag && v.w == flag) return make_uint2(v.x, v.z);
+    return ll_wait_slow(src, flag, sy, code, dead);
+}
 
 // NW warps per CTA, MINB CTAs per SM (register budget), NT 8-token n-tiles, AT live tiles per warp
 // GV: single-token (GEMV) tile code, see decode_tile.cuh
@@ -94,7 +132,11 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     uint32_t epoch = p.sync.epoch;
     bool alt = false;
     uint32_t* epoch_word = reinterpret_cast<uint32_t*>(bars + 1 + MAX_NW * MAX_STAGES + 2 * MAX_NW) + MAX_NW;
-    auto out_ptr = [&](int o) -> __half* { return alt ? p.sync.alt_out[o] : p.outs.p[o]; };
+    __half* c_full = nullptr;   // fused exchange: column 0 of this epoch's full [T, ldc] result (set in stage_x)
+    bool ll_dead = false;       // a cross-GPU wait of this thread has given up
+    auto out_ptr = [&](int o) -> __half* {
+        return (c_full != nullptr && o == 0) ? c_full + static_cast<int64_t>(p.sync.rank) * p.O : p.outs.p[o];
+    };
     // every warp initialises its own barriers (ring stages, cluster mailbox pair) and starts streaming right away; the
     // barrier of the activations (bars[0], warp 0) is first used after the __syncthreads at the top of stage_x
     if (lane == 0) {
@@ -108,6 +150,26 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         fence_mbar_init();
     }
     __syncwarp();
+
+    // fused exchange: send the 16 rows x T tokens of a finished tile (just stored to this rank's C by this warp) to
+    // every peer's landing buffer as LL lines
+    auto ll_send_tile = [&](int tile) {
+        __syncwarp();
+        const int row0 = tile * 16;
+        const int nl = min(16, static_cast<int>(p.O) - row0) >> 2;   // lines per token
+        const int per_lines = static_cast<int>(p.O >> 2);
+        const size_t par_off = static_cast<size_t>(epoch & 1u) * p.sync.c_half_lines;
+        const __half* own = c_full + static_cast<int64_t>(p.sync.rank) * p.O;
+        const int n = p.T * nl;
+        for (int j = lane; j < n * (p.sync.world - 1); j += 32) {
+            const int pr = j / n, rem = j - pr * n;
+            const int t = rem / nl, q = rem - t * nl;
+            const int peer = pr + (pr >= p.sync.rank ? 1 : 0);
+            const uint2 v = __ldcg(reinterpret_cast<const uint2*>(own + static_cast<int64_t>(t) * p.ldc + row0 + 4 * q));
+            ll_store(p.sync.c_land_peer[peer] + par_off + (static_cast<size_t>(p.sync.rank * p.T + t) * per_lines + tile * 4 + q),
+                     v.x, v.y, epoch);
+        }
+    };
 
     const int KW = p.KW, WT = NW / KW, tg = w / KW, sub = w % KW;
     // (K-sliced fallback) live tile `a` of batch `batch` is round batch*AT + a; a round spreads WT tiles over every CTA
@@ -154,6 +216,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                         for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
                     }
                 }
+            if (c_full != nullptr) ll_send_tile(tile);
         }
     };
 
@@ -166,66 +229,67 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     auto stage_x = [&](int slice, bool first) {
         const int e0 = slice * p.cps * G::CHUNK_ELEMS;
         const int ne = min(p.cps * G::CHUNK_ELEMS, p.K - e0);
+        const bool xsync = p.sync.world > 1;
         __syncthreads();  // every warp is done with the previous slice's x / tbl
-        // owner rank: CTA b < world serves peer b (copies the activations into its landing buffer, then raises its ready
-        // word), so the pushes to all peers run in parallel; CTA `rank` raises the word that peers without a landing
-        // buffer poll remotely.  (The grid has >= world CTAs whenever there are >= world tiles; else CTA 0 serves all.)
-        const int nserve = min(static_cast<int>(gridDim.x), p.sync.world);
-        const bool pusher = first && p.sync.x_publish != nullptr && static_cast<int>(blockIdx.x) < nserve;  // CTA-uniform
         if (tid == 0 && first) {
             pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
             if (p.sync.epoch_dev != nullptr)  // written back by the last CTA of the previous launch at its very end
                 epoch = *reinterpret_cast<volatile const uint32_t*>(p.sync.epoch_dev) + 1u;
             *epoch_word = epoch;
         }
-        if (pusher) {
+        if (xsync && first) {
             __syncthreads();
-            const uint32_t e = *epoch_word;
-            const uint8_t* const Xsrc = (p.sync.epoch_dev != nullptr && (e & 1u)) ? p.sync.X_alt : p.X;
-            const int vec_per_row = p.K / 8, ld_vec = static_cast<int>(p.ldx_bytes / 16);
-            const bool all = nserve < p.sync.world;   // too few CTAs: CTA 0 serves every peer
-            for (int r = 0; r < p.sync.world; ++r) {
-                if (!all && r != static_cast<int>(blockIdx.x)) continue;
-                if (all && blockIdx.x != 0) continue;
-                uint4* dst = p.sync.x_push[r];
-                if (dst != nullptr)
-                    for (int i = tid; i < p.T * vec_per_row; i += NW * 32) {
-                        const int t = i / vec_per_row, c = i - t * vec_per_row;
-                        dst[t * ld_vec + c] = reinterpret_cast<const uint4*>(Xsrc)[t * ld_vec + c];
-                    }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();
-                for (int r = 0; r < p.sync.world; ++r) {
-                    if (!all && r != static_cast<int>(blockIdx.x)) continue;
-                    if (all && blockIdx.x != 0) continue;
-                    if (r == p.sync.rank) st_release_sys(p.sync.x_publish, e);   // for peers that pull
-                    else if (p.sync.x_push[r] != nullptr) st_release_sys(p.sync.flags_peer[r] + 8, e);
-                }
-            }
-        }
-        if (tid == 0) {
-            if (first && p.sync.world > 0 && p.sync.x_ready != nullptr) {
-                // activations come from rank 0: wait for the "ready" word of this step
-                while (ld_acquire_sys(p.sync.x_ready) < epoch) {
-                }
-                fence_proxy_async_all();  // the TMA engine (async proxy) reads what we just acquired
-            }
-            const uint8_t* const Xg = (p.sync.epoch_dev != nullptr && (epoch & 1u)) ? p.sync.X_alt : p.X;
-            mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
-            for (int t = 0; t < p.T; ++t)
-                bulk_g2s(xs + t * p.x_stride, Xg + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
-                         static_cast<uint32_t>(ne * 2), &bars[0]);
-        }
-        mbar_wait(&bars[0], x_phase);
-        x_phase ^= 1;
-        stage_activations<FMT, NT, GV>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
-        __syncthreads();
-        if (first) {
             epoch = *epoch_word;
             alt = p.sync.epoch_dev != nullptr && (epoch & 1u) != 0u;
+            c_full = alt ? p.sync.C_alt : p.sync.C_full;
         }
+        const bool owner = !xsync || p.sync.rank == p.sync.x_owner;
+        if (xsync && owner && first) {
+            // owner rank: CTA b < world pushes the activations to peer b as LL lines (data and "it is there" in the same
+            // 16-byte store: one NVLink hop, no fence), so the pushes to all peers run in parallel.  (The grid has >= world
+            // CTAs whenever there are >= world tiles; else CTA 0 serves every peer.)
+            const int nserve = min(static_cast<int>(gridDim.x), p.sync.world);
+            if (static_cast<int>(blockIdx.x) < nserve) {
+                const uint8_t* const Xsrc = alt ? p.sync.X_alt : p.X;
+                const int lpr = p.K >> 2, total = p.T * lpr;
+                const bool all = nserve < p.sync.world;
+                for (int r = 0; r < p.sync.world; ++r) {
+                    if (all ? blockIdx.x != 0 : r != static_cast<int>(blockIdx.x)) continue;
+                    uint4* dst = p.sync.x_land_peer[r];
+                    if (dst == nullptr) continue;
+                    dst += static_cast<size_t>(epoch & 1u) * p.sync.x_half_lines;
+                    for (int i = tid; i < total; i += NW * 32) {
+                        const int t = i / lpr, c = i - t * lpr;
+                        const uint2 v = *reinterpret_cast<const uint2*>(Xsrc + t * p.ldx_bytes + static_cast<int64_t>(c) * 8);
+                        ll_store(dst + i, v.x, v.y, epoch);
+                    }
+                }
+            }
+        }
+        if (owner) {
+            if (tid == 0) {
+                const uint8_t* const Xg = alt ? p.sync.X_alt : p.X;
+                mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(p.T * ne * 2));
+                for (int t = 0; t < p.T; ++t)
+                    bulk_g2s(xs + t * p.x_stride, Xg + t * p.ldx_bytes + 2 * static_cast<int64_t>(e0),
+                             static_cast<uint32_t>(ne * 2), &bars[0]);
+            }
+            mbar_wait(&bars[0], x_phase);
+            x_phase ^= 1;
+        } else {
+            // peers: the activations arrive as LL lines in the local landing buffer; every CTA polls the lines of this
+            // K-slice and unpacks them straight into shared memory
+            const uint4* src = p.sync.x_land + static_cast<size_t>(epoch & 1u) * p.sync.x_half_lines;
+            const int lpr = p.K >> 2, l0 = e0 >> 2, nl = ne >> 2;
+            for (int i = tid; i < p.T * nl; i += NW * 32) {
+                const int t = i / nl, c = i - t * nl;
+                const uint2 v = ll_wait(src + t * lpr + l0 + c, epoch, p.sync, GGQ_SYNC_TIMEOUT_X, ll_dead);
+                *reinterpret_cast<uint2*>(xs + t * p.x_stride + c * 8) = v;
+            }
+            __syncthreads();
+        }
+        stage_activations<FMT, NT, GV>(xs, p.x_stride, tbl, ne, p.T, tid, NW * 32);
+        __syncthreads();
     };
 
     // ---- consume the chunk sitting in ring stage `cstage` (chunk `ci` of K-slice `slice`) -----------
@@ -336,6 +400,16 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         while (pi < iend && pci >= nsc_mine) p_advance();
         for (int s = 0; s < STG && pi < iend; ++s) produce(s);
         if (tid < NW) flags[tid] = 0u;
+        if (p.l2_prefetch_bytes > 0) {
+            // fused exchange: this launch is about to wait — for the previous step's exchange to finish (pdl_wait) and,
+            // on the peers, for the activations to arrive over NVLink.  Pull the head of the CTA's weight range
+            // (contiguous whole rows) into L2 meanwhile, so that HBM streams during those latencies.
+            const uint8_t* base = p.W + static_cast<int64_t>(tile_lo) * 16 * p.rowB;
+            const int64_t row_end = min(static_cast<int64_t>(tile_hi) * 16, p.O);
+            const int64_t total = min((row_end - static_cast<int64_t>(tile_lo) * 16) * p.rowB, static_cast<int64_t>(p.l2_prefetch_bytes));
+            for (int64_t off = static_cast<int64_t>(tid) * 4096; off < total; off += static_cast<int64_t>(NW) * 32 * 4096)
+                prefetch_l2_bulk(base + off, static_cast<uint32_t>(min(static_cast<int64_t>(4096), total - off) & ~int64_t{15}));
+        }
         if (S > 1) cl_sync();     // every CTA of the cluster runs and has initialised its barriers before anyone signals them
         stage_x(crank, true);     // (its barriers also publish the cleared flags inside the CTA)
 
@@ -351,10 +425,10 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                         const __half h = __float2half_rn(acc.v[nt][i]);
                         const int64_t at = col * p.ldc + row;
                         out_ptr(0)[at] = h;
-                        if (!p.bulk_push)
-                            for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
+                        for (int o = 1; o < p.outs.n; ++o) out_ptr(o)[at] = h;
                     }
                 }
+            if (c_full != nullptr) ll_send_tile(tile);
         };
 
         int tile = tile_lo + ibeg / nsc, ci = ibeg % nsc;
@@ -447,23 +521,6 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             }
         }
         if (S > 1) cl_sync();  // nobody writes into the shared memory of a CTA that has exited
-        if (p.bulk_push && p.outs.n > 1) {
-            // fused N-split exchange: this CTA's rows [tile_lo*16, tile_hi*16) of every token are complete in the local
-            // buffer; copy them to the peers as whole 16-byte vectors (an NVLink packet per 128 contiguous bytes instead
-            // of one per 8 rows: the per-tile 2-byte peer stores made the 8-GPU step packet-rate bound)
-            __syncthreads();
-            const int row0 = tile_lo * 16;
-            const int nrows = min(tile_hi * 16, static_cast<int>(p.O)) - row0;
-            const int nvec = nrows / 8;
-            for (int o = 1; o < p.outs.n; ++o)
-                for (int t = 0; t < p.T; ++t) {
-                    const __half* src = out_ptr(0) + t * p.ldc + row0;
-                    __half* dst = out_ptr(o) + t * p.ldc + row0;
-                    for (int i = tid; i < nvec; i += NW * 32)
-                        reinterpret_cast<uint4*>(dst)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
-                    for (int i = nvec * 8 + tid; i < nrows; i += NW * 32) dst[i] = __ldcg(src + i);
-                }
-        }
     } else {
         // ======== K-sliced walk: AT live tiles per warp share each staged activation slice ========
         auto tile_of = [&](int batch, int a) -> int64_t {
@@ -519,23 +576,27 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
     }
 
     if (p.sync.world > 1) {
-        // ---- fused N-split exchange: every tile above was stored into all ranks' C; tell the peers, wait for theirs
-        __syncthreads();          // all stores of this CTA (possibly to peer memory) are issued ...
+        // ---- fused N-split exchange, receive side: the peers' slices arrive as LL lines in this rank's landing buffer;
+        // every CTA polls an equal share of them and writes plain fp16 into C.  When the kernel completes, the full
+        // C[T, world * O] is present in this rank's buffer (nothing else to wait for: no flags, no fence).
+        __syncthreads();
+        const int per_lines = static_cast<int>(p.O >> 2), tl = p.T * per_lines;
+        const int64_t L = static_cast<int64_t>(p.sync.world - 1) * tl;
+        const int64_t lb = static_cast<int64_t>(blockIdx.x) * L / gridDim.x, le = static_cast<int64_t>(blockIdx.x + 1) * L / gridDim.x;
+        const uint4* land = p.sync.c_land + static_cast<size_t>(epoch & 1u) * p.sync.c_half_lines;
+        for (int64_t i = lb + tid; i < le; i += NW * 32) {
+            const int sp = static_cast<int>(i / tl), rem = static_cast<int>(i - static_cast<int64_t>(sp) * tl);
+            const int t = rem / per_lines, q = rem - t * per_lines;
+            const int src = sp + (sp >= p.sync.rank ? 1 : 0);
+            const uint2 v = ll_wait(land + (static_cast<size_t>(src * p.T + t) * per_lines + q), epoch, p.sync, GGQ_SYNC_TIMEOUT_PEER, ll_dead);
+            *reinterpret_cast<uint2*>(c_full + static_cast<int64_t>(t) * p.ldc + static_cast<int64_t>(src) * p.O + 4 * q) = v;
+        }
+        __syncthreads();
         if (tid == 0) {
-            __threadfence_system();   // ... and ordered, at system scope, before the signal below (cumulative over the barrier)
             const uint32_t arrived = atomicAdd(p.sync.counter, 1u) + 1u;
-            if (arrived == p.sync.counter_target) {   // last CTA of this rank
-                __threadfence_system();
-                for (int r = 0; r < p.sync.world; ++r)
-                    if (r != p.sync.rank) st_release_sys(p.sync.flags_peer[r] + p.sync.rank, epoch);
-                for (int r = 0; r < p.sync.world; ++r)
-                    if (r != p.sync.rank)
-                        while (ld_acquire_sys(p.sync.flags_local + r) < epoch) {
-                        }
-                if (p.sync.epoch_dev != nullptr) {  // replayable mode: leave the state ready for the next launch
-                    *p.sync.counter = 0u;
-                    *p.sync.epoch_dev = epoch;
-                }
+            if (arrived == gridDim.x) {   // last CTA of this rank: leave the state ready for the next launch
+                *p.sync.counter = 0u;
+                if (p.sync.epoch_dev != nullptr) *p.sync.epoch_dev = epoch;
             }
         }
     }
@@ -573,7 +634,7 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.nw = NW;
     pl.occ = OCC;
     if (a.sync) p.sync = *a.sync;
-    p.bulk_push = 0;
+    p.l2_prefetch_bytes = 0;
     {
         static const int skip = [] { const char* e = getenv("GGQ_DECODE_NOCOMPUTE"); return (e && e[0] == '1') ? 1 : 0; }();
         p.dbg_skip_compute = skip;
@@ -638,14 +699,11 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
     pl.at = at;
     pl.smem = layout(cps, stages, at, true);
     if (at == 1) {  // flat (tile, chunk) walk: KW is not used, every CTA / cluster owns >= 1 tile
-        static const bool no_bulk = getenv("GGQ_NO_BULK_PUSH") != nullptr;
-        if (a.sync && a.n_out > 1 && a.ldc % 8 == 0 && !no_bulk) {
-            bool aligned = true;
-            for (int i = 0; i < a.n_out; ++i) {
-                aligned = aligned && (reinterpret_cast<uintptr_t>(a.C[i]) & 15) == 0;
-                if (a.sync->epoch_dev) aligned = aligned && (reinterpret_cast<uintptr_t>(a.sync->alt_out[i]) & 15) == 0;
-            }
-            p.bulk_push = aligned ? 1 : 0;
+        if (a.sync && a.sync->world > 1 && S == 1) {
+            // L2 prefetch budget: at most ~56 MB per GPU in flight ahead of the TMA rings (L2 is 126 MB), 4 KB granules
+            static const int mb = [] { const char* e = getenv("GGQ_SYNC_L2_PREFETCH_MB"); return e ? atoi(e) : 56; }();
+            const int64_t per_cta = (static_cast<int64_t>(mb) << 20) / std::max(1, std::min(sms, p.num_tiles));
+            p.l2_prefetch_bytes = static_cast<int>(std::min<int64_t>(per_cta, int64_t{1} << 22)) & ~4095;
         }
         p.KW = 1;
         pl.grid = S * std::max(1, std::min(sms / S, p.num_tiles));
@@ -655,7 +713,6 @@ static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_sl
         const int rounds = (p.num_tiles + pl.grid * wt - 1) / (pl.grid * wt);
         p.num_batches = (rounds + at - 1) / at;
     }
-    if (a.sync) p.sync.counter_target = a.sync->counter_target + static_cast<uint32_t>(pl.grid);  // base + CTAs of this launch
     if (a.ctas_out) *a.ctas_out = pl.grid;
     return true;
 }
@@ -775,7 +832,7 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
 
 template <int FMT>
 static int launch_fmt(const MmArgs& a) {
-    if (a.sync && a.T > 16) return GGQ_E_FAMILY;  // the fused exchange is a single-pass feature
+    if (a.sync && a.T > 8) return GGQ_E_FAMILY;  // the fused exchange is a single-pass, one-n-tile feature
     for (int64_t t0 = 0; t0 < a.T; t0 += 16) {  // T > 16: 16-token passes (weights re-read per pass)
         MmArgs s = a;
         s.X = static_cast<const __half*>(a.X) + t0 * a.ldx;

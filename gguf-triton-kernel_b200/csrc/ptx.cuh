@@ -50,6 +50,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// long waits (the producer of the phase is many steps away): sleep between polls instead of spinning on issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
+// L2 prefetch of `bytes` (multiple of 16) starting at the 16-byte aligned global address p
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- programmatic dependent launch (sm_90+): no-ops when the kernel was launched without the attribute ----
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

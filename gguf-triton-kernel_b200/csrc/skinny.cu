@@ -69,8 +69,12 @@ struct Params {
     uint32_t* flags;        // [grid][4] one word per (CTA, lane quarter): 1 = the partial sums are in the workspace
     long long* prof;        // dev (GGQ_SKINNY_PROF=1): clock64 stamps of CTA 0, [64 steps][16 events]
 };
+#ifdef GGQ_SKINNY_PROF_BUILD   // dev builds only: the stamps cost ~1.5 % of the dequant loop's issue slots
 #define SKN_STAMP(j, ev) \
     do { if (p.prof != nullptr && blockIdx.x == 0 && (j) < 64) p.prof[(j) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define SKN_STAMP(j, ev) do { } while (0)
+#endif
 
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
@@ -206,7 +210,8 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     using C = Cfg<FMT, N, WU, G, MAXT>;
     using U = Unit<FMT>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t{1023});
+    // align through the shared-window offset, not through a generic-pointer cast: the loads below stay LDS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* xring = smem;                                        // [xst][X_STAGE], 1024-byte aligned atoms
     uint8_t* wring = smem + p.xst * C::X_STAGE;                   // [depth][128 rows][ROW_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(wring + p.depth * C::W_SLOT);
@@ -295,8 +300,10 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         while (!cw.done || !cx.done) {
             // test_wait, not try_wait: a try_wait on the ring that is not ready may suspend this warp for microseconds
             // while the other ring starves.  (lap ^ 1 = parity of the previous use of the slot)
-            if (!cx.done && mbar_test_wait(&x_free[xr.idx], xr.lap ^ 1u)) issue_x();
-            if (!cw.done && mbar_test_wait(&w_empty[wr.idx], wr.lap ^ 1u)) issue_w();
+            bool any = false;
+            if (!cx.done && mbar_test_wait(&x_free[xr.idx], xr.lap ^ 1u)) { issue_x(); any = true; }
+            if (!cw.done && mbar_test_wait(&w_empty[wr.idx], wr.lap ^ 1u)) { issue_w(); any = true; }
+            if (!any) __nanosleep(64);   // both rings full: leave the issue slots to the dequant warps
         }
     } else if (warp == C::MMA_WARP) {
         // ================= MMA issuer =================
@@ -372,7 +379,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 if (!mine) continue;
                 if (stamp) SKN_STAMP(step, 5);
                 if (step >= C::NBUF) {
-                    mbar_wait(&a_free[ab], alap ^ 1u);  // the MMAs of step - NBUF have read this buffer
+                    mbar_wait_backoff(&a_free[ab], alap ^ 1u, 32);  // the MMAs of step - NBUF have read this buffer
                     tc_fence_after();
                 }
                 if (stamp) SKN_STAMP(step, 6);
@@ -407,7 +414,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         pdl_wait();  // C (and the workspace) may still be in use by earlier kernels of the stream
         for (uint32_t pt0 = 0, pass = 0; pt0 < ntiles; pt0 += MAXT, ++pass) {
             const uint32_t nt = min(static_cast<uint32_t>(MAXT), ntiles - pt0), accs = pass & 1u;
-            mbar_wait(&acc_full[accs], (pass >> 1) & 1u);
+            mbar_wait_backoff(&acc_full[accs], (pass >> 1) & 1u, 256);  // a whole pass away: do not spin on issue slots
             tc_fence_after();
             for (uint32_t ti = 0; ti < nt; ++ti) {
                 const uint32_t trel = pt0 + ti, tile = tile0 + trel;
@@ -458,9 +465,11 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                                 const __half h = __float2half_rn(__uint_as_float(r[i]));
                                 const int64_t at = static_cast<int64_t>(t) * p.ldc + grow;
                                 p.outs.p[0][at] = h;
+                                if (p.outs.n > 1) {   // uniform branch: the common single-output launch issues one store
 #pragma unroll
-                                for (int o = 1; o < 8; ++o)
-                                    if (o < p.outs.n) p.outs.p[o][at] = h;
+                                    for (int o = 1; o < 8; ++o)
+                                        if (o < p.outs.n) p.outs.p[o][at] = h;
+                                }
                             }
                         }
                     }

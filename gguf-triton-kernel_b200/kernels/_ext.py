@@ -127,29 +127,17 @@ def mm_ex(fmt: int, A: torch.Tensor, B: torch.Tensor, outs: list[int], ldc: int,
 
 class PeerSync(ctypes.Structure):
     """ctypes mirror of `ggq_peer_sync` (include/ggq.h)."""
-    _fields_ = [("flags_local", _P), ("flags_peer", _P * 8), ("counter", _P), ("x_ready", _P),
-                ("epoch", ctypes.c_uint32), ("counter_base", ctypes.c_uint32), ("rank", ctypes.c_int32),
-                ("world", ctypes.c_int32), ("x_publish", _P), ("epoch_dev", _P), ("X_alt", _P), ("C_alt", _P * 8),
-                ("x_push", _P * 8)]
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("x_owner", ctypes.c_int32), ("epoch", ctypes.c_uint32),
+                ("counter", _P), ("epoch_dev", _P), ("X_alt", _P), ("C_alt", _P),
+                ("x_land", _P), ("x_land_peer", _P * 8), ("x_land_half", _I64),
+                ("c_land", _P), ("c_land_peer", _P * 8), ("c_land_half", _I64),
+                ("status", _P), ("timeout_ns", ctypes.c_uint64)]
 
 
-def mm_sync(fmt: int, A: torch.Tensor, x_ptr: int, outs: list[int], ldc: int, M: int, N: int, K: int,
-            sync: PeerSync, *, ldx: int | None = None) -> int:
-    """Decode-family call with the N-split exchange fused into the kernel; returns the CTAs launched."""
-    L = lib()
-    if not hasattr(L, "_sync_ready"):
-        L.ggq_mm_sync.argtypes = [_INT, _P, _P, _I64, ctypes.POINTER(_P), _INT, _I64, _I64, _I64, _I64,
-                                  ctypes.POINTER(PeerSync), ctypes.POINTER(_INT), _P]
-        L.ggq_mm_sync.restype = _INT
-        L._sync_ready = True
-    arr = (_P * len(outs))(*outs)
-    ctas = _INT(0)
-    with torch.cuda.device(A.device):
-        stream = torch.cuda.current_stream().cuda_stream
-        rc = L.ggq_mm_sync(fmt, A.data_ptr(), x_ptr, K if ldx is None else ldx, arr, len(outs), ldc, M, N, K,
-                           ctypes.byref(sync), ctypes.byref(ctas), stream)
-    check(rc, "ggq_mm_sync")
-    return int(ctas.value)
+def bind_mm_sync(L: ctypes.CDLL) -> None:
+    L.ggq_mm_sync.argtypes = [_INT, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, ctypes.POINTER(PeerSync),
+                              ctypes.POINTER(_INT), _P]
+    L.ggq_mm_sync.restype = _INT
 
 
 def dequant(fmt: int, A: torch.Tensor, M: int, K: int) -> torch.Tensor:

@@ -8,15 +8,16 @@ are exchanged so that every rank ends up with the full C[T, O].  Two exchange pa
 
   "nccl"   ncclAllGather of the contiguous [T, O/G] slices into [G, T, O/G], then (T > 1) one transpose
            copy to [T, O].  Baseline path.
-  "fused"  no collective kernel at all: the GEMM/GEMV epilogue stores each output tile straight into the
-           [T, O] buffers of ALL ranks through NVLink peer mappings (torch symmetric memory supplies
-           the peer pointers; the kernels take them as n_out outputs with ldc = O), so the transfer
-           overlaps the math tile by tile.  For T <= 16 the whole exchange lives inside the ONE decode
-           kernel (ggq_mm_sync): ranks != 0 read the activations directly from rank 0's buffer over
-           NVLink after acquiring its "ready" word, and the last CTA of every rank publishes / awaits
-           per-rank epoch flags in peer memory, so kernel completion == C[T, O] complete everywhere.
-           For T > 16 (prefill) the activations are NCCL-broadcast and a symmetric-memory barrier
-           follows the GEMM (its cost is negligible next to a millisecond GEMM).
+  "fused"  no collective kernel at all.
+           T <= 8 (and T*K <= 65536): the whole step is ONE decode kernel per rank (ggq_mm_sync).  Rank 0's kernel
+           pushes the activations to the peers and every rank sends its finished output tiles to all peers as
+           flag-in-data lines (16-byte stores carrying 4 fp16 + the step's epoch) into peer-mapped landing buffers
+           (torch symmetric memory supplies the NVLink mappings); the receivers poll the lines themselves, so each
+           transfer is one NVLink hop with no fence and no flag round trip, and kernel completion == C[T, O] complete
+           on this rank.  The epoch lives in device memory, so a step is CUDA-graph capturable.
+           More tokens: NCCL broadcast of X, then the GEMM (tcgen05 skinny / prefill kernels) peer-stores each output
+           tile into the [T, O] buffers of ALL ranks (n_out outputs with ldc = O), between two symmetric-memory
+           barriers.
 
 `mm_fn` is injectable so the host logic (sharding arithmetic, exchange layout) is testable on CPU with
 the gloo backend and a stand-in matmul.
@@ -64,8 +65,10 @@ def assemble(gathered: torch.Tensor) -> torch.Tensor:
 
 
 class NSplitLinear:
+    DECODE_MAX_T = 8   # fused decode kernel for T <= 8; 9..16 tokens take the GEMM path (tcgen05 skinny kernel + peer stores)
+
     def __init__(self, fmt: str, A_shard: torch.Tensor, O: int, K: int, *, group=None, mode: str = "nccl",
-                 max_tokens: int = 16, mm_fn: Callable | None = None):
+                 max_tokens: int = 16, mm_fn: Callable | None = None, sync_timeout_s: float = 2.0):
         self.fmt, self.O, self.K = fmt, O, K
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -78,7 +81,9 @@ class NSplitLinear:
         self.mode = mode
         self.max_tokens = max_tokens
         self.mm_fn = mm_fn
+        self.sync_timeout_s = sync_timeout_s   # bound of every cross-GPU wait inside the fused decode kernel
         self._symm = None
+        self._after_gemm = False   # the last fused call was a T > 16 GEMM (wrote buffer 0 outside the decode parity rule)
         if mm_fn is None:
             from kernels import _ext  # the CUDA library; raises if it is not built (no fallback)
             self._ext = _ext
@@ -89,21 +94,31 @@ class NSplitLinear:
             raise ValueError(mode)
 
     # ---- fused path: peer-mapped buffers ----
+    LL_MAX_TK = 65536   # T * K limit of the fused decode kernel (every CTA of a peer polls all activation lines)
+
     def _init_symm(self):
         import torch.distributed._symmetric_memory as symm_mem
         dev = self.A.device
+        # GEMM path (T > DECODE_MAX_T): the epilogue peer-stores tiles into buffer 0 of every rank; decode path: local only
         self._out = symm_mem.empty((2, self.max_tokens, self.O), dtype=torch.float16, device=dev)   # double-buffered C
         self._symm = symm_mem.rendezvous(self._out, self.group)
-        self._xbuf = symm_mem.empty((2, min(self.max_tokens, 16), self.K), dtype=torch.float16, device=dev)
-        self._xsymm = symm_mem.rendezvous(self._xbuf, self.group)
-        self._flags = symm_mem.empty((16,), dtype=torch.int32, device=dev)  # [0..7] peer epochs, [8] x ready
-        self._flags.zero_()
-        self._fsymm = symm_mem.rendezvous(self._flags, self.group)
+        tcap = self.DECODE_MAX_T
+        self._xbuf = torch.zeros((2, tcap, self.K), dtype=torch.float16, device=dev)    # rank 0: the step's activations
+        # landing buffers of the flag-in-data exchange (16-byte lines carrying 4 fp16): two epoch-parity halves each
+        self._x_half = min(tcap * self.K, self.LL_MAX_TK) * 4
+        self._xland = symm_mem.empty((2 * self._x_half,), dtype=torch.uint8, device=dev)
+        self._xland.zero_()
+        self._xlsymm = symm_mem.rendezvous(self._xland, self.group)
+        self._c_half = self.world * tcap * self.per * 4
+        self._cland = symm_mem.empty((2 * self._c_half,), dtype=torch.uint8, device=dev)
+        self._cland.zero_()
+        self._clsymm = symm_mem.rendezvous(self._cland, self.group)
         self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # kernel-maintained epoch (replayable mode)
         self._epoch = 0                                                   # host mirror of it
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)      # GGQ_SYNC_* code of a wait that gave up
         torch.cuda.synchronize(dev)
-        self._symm.barrier(channel=0)  # everyone's flags are zeroed before anyone signals
+        self._symm.barrier(channel=0)  # everyone's landing buffers are zeroed before anyone sends
         self._prepare_fast_path()
 
     def _out_ptrs(self, cur: int) -> list[int]:
@@ -117,53 +132,48 @@ class NSplitLinear:
         import ctypes
         ext = self._ext
         self._lib = ext.lib()
-        self._lib.ggq_mm_sync.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
-                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
-                                          ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ext.PeerSync),
-                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
-        self._lib.ggq_mm_sync.restype = ctypes.c_int
-        self._out_arr = [(ctypes.c_void_p * self.world)(*self._out_ptrs(c)) for c in (0, 1)]
-        xrows = self._xbuf.shape[1]
-        self._x_local = [self._xbuf.data_ptr() + c * xrows * self.K * 2 for c in (0, 1)]
+        ext.bind_mm_sync(self._lib)
+        self._c_local = [self._out[c].data_ptr() for c in (0, 1)]          # column 0 of this rank's [T, O] results
+        self._x_local = [self._xbuf[c].data_ptr() for c in (0, 1)]
         sync = ext.PeerSync()
-        sync.flags_local = self._flags.data_ptr()
-        for r in range(self.world):
-            sync.flags_peer[r] = int(self._fsymm.buffer_ptrs[r])
+        sync.rank, sync.world, sync.x_owner = self.rank, self.world, 0
         sync.counter = self._counter.data_ptr()
-        sync.rank, sync.world = self.rank, self.world
         # replayable mode: the kernel keeps the epoch, even epochs use buffer set 0, odd epochs buffer set 1; nothing
         # in the call changes from step to step, so a step can be captured in a CUDA graph
         sync.epoch_dev = self._epoch_dev.data_ptr()
-        for i, ptr in enumerate(self._out_ptrs(1)):
-            sync.C_alt[i] = ptr
-        if self.rank == 0:
-            # the owner's kernel pushes the activations into slot 0 of every peer's symmetric buffer and raises word 8
-            # of the peer's flags; the peers poll and read local memory
-            sync.x_publish, sync.x_ready = self._flags.data_ptr() + 8 * 4, 0
-            self._x_even, sync.X_alt = self._x_local[0], self._x_local[1]
-            for r in range(1, self.world):
-                sync.x_push[r] = int(self._xsymm.buffer_ptrs[r])
-        else:
-            sync.x_publish, sync.x_ready = 0, self._flags.data_ptr() + 8 * 4
-            self._x_even = sync.X_alt = self._x_local[0]
+        sync.X_alt = self._x_local[1]
+        sync.C_alt = self._c_local[1]
+        sync.x_land = self._xland.data_ptr()
+        sync.c_land = self._cland.data_ptr()
+        sync.x_land_half, sync.c_land_half = self._x_half, self._c_half
+        for r in range(self.world):
+            sync.x_land_peer[r] = int(self._xlsymm.buffer_ptrs[r])
+            sync.c_land_peer[r] = int(self._clsymm.buffer_ptrs[r])
+        sync.status = self._status.data_ptr()
+        sync.timeout_ns = int(self.sync_timeout_s * 1e9)
         self._sync = sync
         self._sync_ref = ctypes.byref(sync)
         self._ctas = ctypes.c_int(0)
         self._ctas_ref = ctypes.byref(self._ctas)
         self._a_ptr = self.A.data_ptr()
 
+    def fused_decode_ok(self, T: int) -> bool:
+        """Can T tokens take the one-kernel fused decode step?"""
+        return (self.mode == "fused" and self.world > 1 and T <= self.DECODE_MAX_T and T * self.K <= self.LL_MAX_TK
+                and self.per >= 16 and self.per % 4 == 0 and self.K % 4 == 0)
+
     def input_buffer(self, T: int) -> torch.Tensor:
-        """Rank 0: the symmetric [T, K] buffer the NEXT fused decode step reads its activations from.  Writing the
-        activations there directly (e.g. as the H2D copy target) and calling forward(None, T=T) skips the staging copy."""
+        """Rank 0: the [T, K] buffer the NEXT fused decode step reads its activations from.  Writing the activations
+        there directly (e.g. as the H2D copy target) and calling forward(None, T=T) skips the staging copy."""
         return self._xbuf[(self._epoch + 1) & 1, :T]
 
     def set_resident_input(self, X: torch.Tensor) -> None:
-        """Rank 0: keep the same activations resident in both symmetric slots (benchmarking `forward(None, T=T)`)."""
+        """Rank 0: keep the same activations resident in both slots (benchmarking `forward(None, T=T)`)."""
         self._xbuf[:, :X.shape[0]].copy_(X)
 
     def _launch_sync(self, T: int) -> None:
-        """One fused step with the activations in the symmetric buffer of rank 0 (static arguments: graph-capturable)."""
-        rc = self._lib.ggq_mm_sync(self._fmt_id, self._a_ptr, self._x_even, self.K, self._out_arr[0], self.world, self.O,
+        """One fused step with the activations in rank 0's buffer (static arguments: graph-capturable)."""
+        rc = self._lib.ggq_mm_sync(self._fmt_id, self._a_ptr, self._x_local[0], self.K, self._c_local[0], self.O,
                                    self.per, T, self.K, self._sync_ref, self._ctas_ref,
                                    torch.cuda.current_stream().cuda_stream)
         if rc != 0:
@@ -180,10 +190,10 @@ class NSplitLinear:
         return self._out[cur, :T]
 
     def capture_steps(self, T: int, n: int):
-        """CUDA graph of `n` consecutive fused decode steps on the activations resident in rank 0's symmetric buffer
+        """CUDA graph of `n` consecutive fused decode steps on the activations resident in rank 0's buffer
         (set_resident_input / input_buffer).  Returns replay(): every rank must replay the same number of times;
         last_output(T) is the result of the last step."""
-        if not (self.mode == "fused" and self.world > 1 and T <= 16 and self.per >= 16):
+        if not self.fused_decode_ok(T):
             raise ValueError("capture_steps needs the fused decode path")
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -196,6 +206,16 @@ class NSplitLinear:
             self._epoch += n
         return replay
 
+    def sync_status(self) -> int:
+        """0, or the GGQ_SYNC_* code of the first cross-GPU wait of a fused decode step that gave up after
+        `sync_timeout_s` (1: the activations never arrived, 2: a peer's epoch flag never arrived — a rank did not make
+        the matching call).  Synchronises the stream."""
+        return int(self._status.item()) if self.mode == "fused" else 0
+
+    def _src_rank(self) -> int:
+        """Global rank of the group's rank 0 (dist.broadcast takes global ranks)."""
+        return 0 if self.group is dist.group.WORLD else dist.get_global_rank(self.group, 0)
+
     def last_output(self, T: int) -> torch.Tensor:
         return self._out[self._epoch & 1, :T]
 
@@ -206,17 +226,24 @@ class NSplitLinear:
         if self.mode == "fused":
             if T > self.max_tokens:
                 raise ValueError(f"T={T} exceeds max_tokens={self.max_tokens} of the symmetric buffer")
-            if T <= 16 and self.per >= 16 and broadcast and self.world > 1:
+            if self.fused_decode_ok(T) and broadcast:
+                if self._after_gemm:
+                    # the previous call wrote buffer 0 outside the decode path's even/odd discipline: every rank must be
+                    # done reading that result before any rank's decode kernel peer-stores into buffer 0 again
+                    self._symm.barrier(channel=0)
+                    self._after_gemm = False
                 return self._forward_fused_decode(X, T, broadcast)
+            if X is None:
+                raise ValueError("forward(None, T=...) is the fused decode path only (fused_decode_ok(T))")
             if broadcast and self.world > 1:
-                dist.broadcast(X, src=0, group=self.group)
+                dist.broadcast(X, src=self._src_rank(), group=self.group)
             self._symm.barrier(channel=0)   # every rank has finished reading the previous result
             self._ext.mm_ex(self._fmt_id, self.A, X, self._out_ptrs(0), self.O, self.per, T, self.K)
             self._symm.barrier(channel=1)   # every rank's tiles have landed everywhere
+            self._after_gemm = True
             return self._out[0, :T]
         if broadcast and self.world > 1:
-            dist.broadcast(X, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
-                           group=self.group)
+            dist.broadcast(X, src=self._src_rank(), group=self.group)
         if self.mm_fn is not None:
             c = self.mm_fn(self.A, X, self.per, T, self.K)
         else:

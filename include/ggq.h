@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 105 /* 0.1.5 */
+#define GGQ_VERSION 107 /* 0.1.7 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -82,48 +82,57 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
               int64_t O, int64_t T, int64_t K, int family, void* stream);
 
 /*
- * Decode-family GEMV/skinny GEMM with the N-split exchange fused INTO the kernel (T <= 16):
- *   - activations may live in another rank's memory (X = NVLink peer pointer to rank 0's buffer); if
- *     `x_ready` is non-NULL every CTA first waits until *x_ready >= epoch (acquire, system scope); the owning
- *     rank's kernel raises that word itself when `x_publish` is set;
- *   - every output tile is stored to all C_out[i] (own + peer [T, ldc] buffers);
- *   - at the end the last CTA publishes `epoch` into flags_peer[p][rank] of every peer (release, system
- *     scope) and waits until every peer has published its own into flags_local[p]: when the kernel
- *     completes, the full C[T, O] is present in this rank's buffer.  No NCCL call, no separate barrier kernel.
- * flags_local / flags_peer[p] are uint32[8] arrays in symmetric (peer-mapped) memory, zero-initialised;
- * `counter` is a zero-initialised uint32 in local device memory; `epoch` must increase by 1 per call on all
- * ranks; `counter_base` is the value of *counter before this call (the library adds the grid size).
- * Every rank of the group must make the matching call or the waiting ranks never finish.
+ * Decode-family GEMV/skinny GEMM with the N-split exchange fused INTO the kernel (T <= 8, T*K <= 65536):
+ * ONE kernel per rank and step, no NCCL call, no barrier kernel, no system-scope fence.  Both transfers use a
+ * flag-in-data ("LL") line format: a 16-byte line {data0, epoch, data1, epoch} carries 4 fp16 values and is written
+ * with one 16-byte store over NVLink; the receiver polls the line itself, so data and "it is there" arrive in the
+ * same NVLink hop.
+ *   - activations: the owner rank (x_owner) reads X from its own memory and pushes it as lines into every peer's
+ *     x_land buffer; the peers' CTAs poll their local x_land and unpack straight into shared memory;
+ *   - outputs: every finished 16-row tile is stored to this rank's C and sent as lines into every peer's c_land; at
+ *     the end every CTA polls its share of the lines addressed to this rank and writes them into C as plain fp16:
+ *     when the kernel completes, the full C[T, world * O] is present in this rank's buffer.
+ * W holds this rank's O rows.  `C` points at column 0 of this rank's [T, ldc] result (ldc >= world * O); the rank's
+ * own columns start at rank * O.  O % 4 == 0 and K % 4 == 0.
+ * Landing buffers live in peer-mapped (symmetric) memory, zero-initialised once: x_land = 2 halves (epoch parity) of
+ * `x_land_half` bytes each, >= T*K*4; c_land = 2 halves of `c_land_half` bytes each, >= world*T*O*4.
+ * `epoch` (>= 1) must increase by 1 per call on all ranks; `counter` is a zero-initialised uint32 in local device
+ * memory.  Every rank of the group must make the matching call: a rank that waits in vain gives up after
+ * `timeout_ns` (see `status`).
  */
 typedef struct ggq_peer_sync {
-    uint32_t* flags_local;
-    uint32_t* flags_peer[8];
-    uint32_t* counter;
-    const uint32_t* x_ready;
-    uint32_t epoch;
-    uint32_t counter_base;
     int32_t rank, world;
-    uint32_t* x_publish; /* rank that OWNS the activations: its "ready" word (the one the peers pass as x_ready); the
-                            kernel stores `epoch` there when it starts (the activations were written earlier in
-                            stream order), so no separate flag kernel is needed.  NULL on the other ranks. */
+    int32_t x_owner;       /* rank whose X is the step's activations */
+    uint32_t epoch;        /* this call's epoch (ignored in replayable mode) */
+    uint32_t* counter;     /* local: CTAs that finished this call (the kernel resets it) */
     /* Replayable mode (epoch_dev != NULL): nothing in the call changes from step to step, so the launch can be
-     * captured in a CUDA graph and replayed.  `epoch` and `counter_base` are ignored: the epoch of a call is
-     * *epoch_dev + 1, read by the kernel; the last CTA writes it back and resets *counter to 0 when the exchange is
-     * complete.  Calls with an EVEN epoch use (X, C_out), calls with an ODD epoch use (X_alt, C_alt): the output
+     * captured in a CUDA graph and replayed.  The epoch of a call is *epoch_dev + 1, read by the kernel; the last CTA
+     * writes it back.  Calls with an EVEN epoch use (X, C), calls with an ODD epoch use (X_alt, C_alt): the output
      * double buffering that keeps a fast rank from overwriting results a slow rank's consumer is still reading. */
     uint32_t* epoch_dev;   /* device word, zero-initialised, local to this rank */
-    const void* X_alt;
-    void* C_alt[8];
-    /* Owner rank only (x_publish != NULL), optional: peer-mapped [T, ldx] landing buffers of the other ranks, indexed
-     * like flags_peer (own entry ignored).  When x_push[r] is set the owner's kernel COPIES the activations into rank
-     * r's buffer and then raises word 8 of rank r's flags array, so rank r passes its own local buffer as X and its own
-     * flags_local + 8 as x_ready: it polls and reads local memory instead of crossing NVLink twice. */
-    void* x_push[8];
+    const void* X_alt;     /* owner rank only */
+    void* C_alt;
+    void* x_land;          /* this rank's landing buffer for the activations (unused on the owner) */
+    void* x_land_peer[8];  /* owner rank: the peers' x_land (own entry ignored) */
+    int64_t x_land_half;   /* bytes of one parity half of x_land */
+    void* c_land;          /* this rank's landing buffer for the peers' output slices */
+    void* c_land_peer[8];  /* the peers' c_land (own entry ignored) */
+    int64_t c_land_half;   /* bytes of one parity half of c_land */
+    /* Bounded waits: every poll of a line that has not arrived gives up after `timeout_ns` nanoseconds of the
+     * device's global timer (0 = the default of 2 s).  A wait that gives up stores a GGQ_SYNC_* code (first one wins)
+     * into *status — a zero-initialised uint32 in local device memory, may be NULL — and the kernel runs to completion
+     * with whatever arrived, so a missing or late rank costs a bounded time and is reported instead of hanging the
+     * GPU.  The results of a step whose *status is non-zero are undefined. */
+    uint32_t* status;
+    uint64_t timeout_ns;
 } ggq_peer_sync;
+#define GGQ_SYNC_OK 0u
+#define GGQ_SYNC_TIMEOUT_X 1u     /* the activations did not arrive */
+#define GGQ_SYNC_TIMEOUT_PEER 2u  /* a peer's output lines did not arrive */
 
-/* Returns 0 and writes the number of CTAs launched to *ctas_out (the caller advances counter_base by it). */
-int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc,
-                int64_t O, int64_t T, int64_t K, const ggq_peer_sync* sync, int* ctas_out, void* stream);
+/* Returns 0 and writes the number of CTAs launched to *ctas_out. */
+int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* C, int64_t ldc, int64_t O, int64_t T, int64_t K,
+                const ggq_peer_sync* sync, int* ctas_out, void* stream);
 
 /*
  * Dequantize packed rows to fp16 [O, K] with the SAME device functions the prefill GEMM uses.

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_queries():
     from kernels import _ext
     L = _ext.lib()
-    assert L.ggq_version() == 105
+    assert L.ggq_version() == 107
     assert L.ggq_packed_nbytes(0, 4096, 4096) == 17825792          # BASELINE config 1
     assert L.ggq_packed_nbytes(1, 128256, 4096) == 295501824       # config 2
     assert L.ggq_packed_nbytes(2, 4096, 14336) == 48168960         # config 3
@@ -45,7 +45,8 @@ def test_host_queries():
     assert L.ggq_select_family(1, 128256, 16, 4096) == _ext.FAMILY_SKINNY
     assert L.ggq_select_family(1, 128256, 8, 4096) == _ext.FAMILY_DECODE
     assert L.ggq_select_family(0, 28672, 8, 8192) == _ext.FAMILY_SKINNY
-    assert L.ggq_select_family(2, 128256, 16, 4096) == _ext.FAMILY_DECODE
+    assert L.ggq_select_family(2, 128256, 16, 4096) == _ext.FAMILY_SKINNY
+    assert L.ggq_select_family(2, 128256, 8, 4096) == _ext.FAMILY_DECODE
     assert L.ggq_select_family(1, 4096, 16, 4096) == _ext.FAMILY_DECODE   # small layer: lower fixed cost
     assert b"shape" in L.ggq_error_string(-1)
     assert L.ggq_launch_count() == 0

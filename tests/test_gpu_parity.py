@@ -357,29 +357,95 @@ def test_mm_ex_strides_and_multiple_outputs(ext, fmt, family, N):
     check_tier1(fmt, A, X, M, N, K, C1[:, :M].cpu().numpy(), "mm_ex")
 
 
-@pytest.mark.parametrize("fmt", FMTS)
-def test_mm_sync_single_rank(ext, fmt):
-    """ggq_mm_sync with world = 1: the in-kernel epoch/flag machinery degenerates to a plain call."""
-    M, N, K = 300, 3, 2048
-    A = orc.random_blocks(fmt, M, K, seed=31)
-    X = rand_x(N, K, 32)
-    Ad, Xd = dev(A), dev(X)
-    C = torch.zeros((N, M), dtype=torch.float16, device="cuda:0")
-    flags = torch.zeros(16, dtype=torch.int32, device="cuda:0")
-    counter = torch.zeros(1, dtype=torch.int32, device="cuda:0")
-    sync = ext.PeerSync()
-    sync.flags_local = flags.data_ptr()
-    sync.flags_peer[0] = flags.data_ptr()
-    sync.counter = counter.data_ptr()
-    sync.x_ready = 0
-    sync.rank, sync.world = 0, 1
-    base = 0
-    for epoch in (1, 2, 3):
-        sync.epoch, sync.counter_base = epoch, base
-        base += ext.mm_sync(ext.FMT_ID[fmt], Ad, Xd.data_ptr(), [C.data_ptr()], M, M, N, K, sync)
+def _loopback_ranks(ext, fmt, world, per, N, K, A, X, *, replayable, timeout_s=2.0):
+    """The fused N-split exchange with all `world` ranks on ONE GPU: every rank has its own stream, landing buffers and
+    result buffers, and the "peer" pointers are simply the other ranks' buffers.  The shards are small enough for all
+    ranks' persistent kernels to be co-resident (a rank waits for its peers' lines inside the kernel)."""
+    import ctypes
+    L = ext.lib()
+    ext.bind_mm_sync(L)
+    f = ext.FMT_ID[fmt]
+    O = world * per
+    rb = orc.packed_nbytes(fmt, 1, K)
+    Ad = dev(A)
+    shards = [Ad[r * per * rb:(r + 1) * per * rb].clone() for r in range(world)]
+    x_half, c_half = N * K * 4, world * N * per * 4
+    xs = [dev(X), dev(X * 0.5)]                                                 # rank 0: even / odd epochs
+    xland = [torch.zeros(2 * x_half, dtype=torch.uint8, device="cuda:0") for _ in range(world)]
+    cland = [torch.zeros(2 * c_half, dtype=torch.uint8, device="cuda:0") for _ in range(world)]
+    C = [[torch.zeros((N, O), dtype=torch.float16, device="cuda:0") for _ in range(2)] for _ in range(world)]
+    counter = [torch.zeros(1, dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    epoch_dev = [torch.zeros(1, dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    status = [torch.zeros(1, dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    syncs = []
+    for r in range(world):
+        sy = ext.PeerSync()
+        sy.rank, sy.world, sy.x_owner = r, world, 0
+        sy.counter = counter[r].data_ptr()
+        if replayable:
+            sy.epoch_dev = epoch_dev[r].data_ptr()
+            sy.X_alt = xs[1].data_ptr()
+            sy.C_alt = C[r][1].data_ptr()
+        sy.x_land, sy.c_land = xland[r].data_ptr(), cland[r].data_ptr()
+        sy.x_land_half, sy.c_land_half = x_half, c_half
+        for q in range(world):
+            sy.x_land_peer[q] = xland[q].data_ptr()
+            sy.c_land_peer[q] = cland[q].data_ptr()
+        sy.status = status[r].data_ptr()
+        sy.timeout_ns = int(timeout_s * 1e9)
+        syncs.append(sy)
     torch.cuda.synchronize()
-    assert base > 0 and counter.item() == 0  # a single rank has nobody to signal: the tail is skipped entirely
-    check_tier1(fmt, A, X, M, N, K, C.cpu().numpy(), "mm_sync")
+
+    def step(epoch, ranks=range(world)):
+        for r in ranks:
+            syncs[r].epoch = epoch
+            ctas = ctypes.c_int(0)
+            rc = L.ggq_mm_sync(f, shards[r].data_ptr(), xs[0].data_ptr(), K, C[r][0].data_ptr(), O, per, N, K,
+                               ctypes.byref(syncs[r]), ctypes.byref(ctas), streams[r].cuda_stream)
+            assert rc == 0 and ctas.value > 0, (rc, ctas.value)
+    return step, C, status, xs
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("world,N,replayable", [(2, 1, False), (4, 3, True), (8, 1, True), (3, 8, True)])
+def test_mm_sync_loopback_exchange(ext, fmt, world, N, replayable):
+    """ggq_mm_sync's in-kernel exchange (activation push + output lines, flag-in-data) with every rank on this GPU."""
+    per, K = 64, 2048
+    O = world * per
+    A = orc.random_blocks(fmt, O, K, seed=31)
+    X = rand_x(N, K, 32)
+    step, C, status, xs = _loopback_ranks(ext, fmt, world, per, N, K, A, X, replayable=replayable)
+    for epoch in (1, 2, 3, 4, 5):
+        step(epoch)
+    torch.cuda.synchronize()
+    assert all(int(s.item()) == 0 for s in status)
+    # epoch 5 is odd: in replayable mode it used (X_alt, C_alt) = (0.5 X, buffer 1); epoch 4 used (X, buffer 0)
+    for r in range(world):
+        if replayable:
+            check_tier1(fmt, A, xs[1].cpu().numpy(), O, N, K, C[r][1].cpu().numpy(), f"loopback odd rank {r}")
+        check_tier1(fmt, A, X, O, N, K, C[r][0].cpu().numpy(), f"loopback even rank {r}")
+    for r in range(1, world):   # every rank holds the same bits
+        assert torch.equal(C[r][0], C[0][0])
+
+
+def test_mm_sync_missing_rank_gives_up_with_status(ext):
+    """A rank whose peer never makes the matching call: bounded time, GGQ_SYNC_TIMEOUT_* in *status, no hang."""
+    import time
+    fmt, world, per, N, K = "q8_0", 2, 64, 1, 1024
+    A = orc.random_blocks(fmt, world * per, K, seed=33)
+    step, C, status, _ = _loopback_ranks(ext, fmt, world, per, N, K, A, rand_x(N, K, 34), replayable=False, timeout_s=0.2)
+    step(1)
+    torch.cuda.synchronize()
+    assert int(status[0].item()) == 0 and int(status[1].item()) == 0
+    t0 = time.perf_counter()
+    step(2, ranks=[0])            # rank 1 stays away: rank 0 (the owner) never receives its output lines
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0
+    assert int(status[0].item()) == 2   # GGQ_SYNC_TIMEOUT_PEER
+    step(3, ranks=[1])            # and a peer without its owner never receives the activations
+    torch.cuda.synchronize()
+    assert int(status[1].item()) == 1   # GGQ_SYNC_TIMEOUT_X
 
 
 @pytest.mark.parametrize("fmt", FMTS)

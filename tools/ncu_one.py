@@ -1,15 +1,16 @@
-"""dev helper: launch one decode shape a few times (target of an ncu capture). FMT/O/K/T from env."""
-import sys, os, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/gguf-triton-kernel_b200")
-import bench
+"""dev helper: launch one shape a few times (target of an ncu capture). FMT/O/K/T/FAMILY from env."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gguf-triton-kernel_b200"), os.path.join(ROOT, "tools")):
+    sys.path.insert(0, p)
+import torch
 from kernels import _ext as ext
-v = os.environ.get("GGQ_VARIANT", "")
-if v:
-    ext._LIB_PATH = f"/root/repo/build_variants/libggq_{v}.so"
+from dev_skinny import gen_weights
 fmt = os.environ.get("FMT", "q4_k"); o = int(os.environ.get("O", 128256)); k = int(os.environ.get("K", 4096)); t = int(os.environ.get("T", 1))
-W = bench.gen_weights(torch, fmt, o, k, "cuda", 1)
+fam = int(os.environ.get("FAMILY", 0))
+W = gen_weights(fmt, o, k, 1)
 X = torch.randn((t, k), device="cuda", dtype=torch.float16); C = torch.empty((t, o), device="cuda", dtype=torch.float16)
 for _ in range(6):
-    ext.mm(ext.FMT_ID[fmt], W, X, o, t, k, out=C)
+    ext.mm(ext.FMT_ID[fmt], W, X, o, t, k, out=C, family=fam)
 torch.cuda.synchronize()
 print("done")
