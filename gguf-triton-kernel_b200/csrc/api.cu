@@ -276,6 +276,8 @@ int ggq_describe(int fmt, int64_t O, int64_t T, int64_t K, char* out, int cap) {
     return GGQ_E_FAMILY;
 }
 
+void ggq_dev_set_trace(void* buf) { decode_set_trace(buf); }
+
 int64_t ggq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* ggq_error_string(int code) {

@@ -61,6 +61,7 @@ bool decode_supports(int fmt, const MmArgs& a);
 bool prefill_supports(int fmt, const MmArgs& a);
 bool skinny_supports(int fmt, const MmArgs& a);
 int decode_plan(int fmt, const MmArgs& a, int* out9);
+void decode_set_trace(void* buf);
 int skinny_describe(int fmt, const MmArgs& a, char* out, int cap);
 
 int launch_dequant(int fmt, const uint8_t* W, void* out, int64_t O, int64_t K, cudaStream_t s);

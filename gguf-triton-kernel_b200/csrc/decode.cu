@@ -56,6 +56,7 @@ struct Params {
     int num_batches;
     int stages;
     int l2_prefetch_bytes; // fused exchange: bytes of the CTA's weight range prefetched into L2 before the first wait
+    unsigned long long* trace;  // dev (ggq_dev_set_trace): per-CTA globaltimer stamps of this launch, [grid][8], or null
     int dbg_skip_compute;  // GGQ_DECODE_NOCOMPUTE=1: stream the weights through the TMA rings but skip the math (roofline probe)
     PeerSync sync;      // world == 0: no cross-GPU synchronisation
     uint32_t x_stride;  // bytes between token rows in shared memory
@@ -126,6 +127,16 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 
     // Programmatic dependent launch: the next kernel in the stream may start its own prologue (barrier init, weight
     // prefetch) while this one runs; everything that depends on earlier kernels sits behind pdl_wait() in stage_x.
+    // dev: phase stamps (0 entry, 1 barriers + first boxes issued, 2 pdl_wait passed, 3 activations staged, 4 warp 0's
+    // items done, 5 CTA done)
+    auto stamp = [&](int ev) {
+        if (p.trace != nullptr && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[blockIdx.x * 8 + ev] = t;
+        }
+    };
+    stamp(0);
     pdl_launch_dependents();
     // cross-GPU exchange: the epoch of this launch (host-supplied, or kernel-maintained in replayable mode, where odd
     // epochs use the alternate activation / output buffers); settled in stage_x once the previous kernel is complete
@@ -233,6 +244,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         __syncthreads();  // every warp is done with the previous slice's x / tbl
         if (tid == 0 && first) {
             pdl_wait();  // earlier kernels in the stream (the producers of X, earlier users of C) are complete
+            stamp(2);
             if (p.sync.epoch_dev != nullptr)  // written back by the last CTA of the previous launch at its very end
                 epoch = *reinterpret_cast<volatile const uint32_t*>(p.sync.epoch_dev) + 1u;
             *epoch_word = epoch;
@@ -411,7 +423,9 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
                 prefetch_l2_bulk(base + off, static_cast<uint32_t>(min(static_cast<int64_t>(4096), total - off) & ~int64_t{15}));
         }
         if (S > 1) cl_sync();     // every CTA of the cluster runs and has initialised its barriers before anyone signals them
+        stamp(1);
         stage_x(crank, true);     // (its barriers also publish the cleared flags inside the CTA)
+        stamp(3);
 
         auto store_tile = [&](int tile, const Acc<NT>& acc) {
 #pragma unroll
@@ -575,6 +589,11 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
         }
     }
 
+    stamp(4);
+    if (p.trace != nullptr && p.sync.world <= 1) {
+        __syncthreads();
+        stamp(5);
+    }
     if (p.sync.world > 1) {
         // ---- fused N-split exchange, receive side: the peers' slices arrive as LL lines in this rank's landing buffer;
         // every CTA polls an equal share of them and writes plain fp16 into C.  When the kernel completes, the full
@@ -592,6 +611,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
             *reinterpret_cast<uint2*>(c_full + static_cast<int64_t>(t) * p.ldc + static_cast<int64_t>(src) * p.O + 4 * q) = v;
         }
         __syncthreads();
+        stamp(5);
         if (tid == 0) {
             const uint32_t arrived = atomicAdd(p.sync.counter, 1u) + 1u;
             if (arrived == gridDim.x) {   // last CTA of this rank: leave the state ready for the next launch
@@ -603,6 +623,9 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+static unsigned long long* g_trace = nullptr;   // dev: [16 launches][320 CTAs][8 stamps] device buffer (ggq_dev_set_trace)
+static unsigned g_trace_n = 0;
+
 struct Plan {
     Params p;
     int nt, at, grid, nw, occ;
@@ -825,7 +848,9 @@ static int launch_kernel(const Plan& pl, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, map_w, pl.p);
+    Params prm = pl.p;
+    if (g_trace != nullptr) prm.trace = g_trace + static_cast<size_t>(g_trace_n++ % 16) * (320 * 8);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, map_w, prm);
     count_launch();
     return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
@@ -861,6 +886,11 @@ static int launch_fmt(const MmArgs& a) {
 }
 
 }  // namespace dec
+
+void decode_set_trace(void* buf) {
+    dec::g_trace = static_cast<unsigned long long*>(buf);
+    dec::g_trace_n = 0;
+}
 
 bool decode_supports(int fmt, const MmArgs& a) {
     if (a.T < 1 || a.O < 1 || a.K < fmt_qk(fmt)) return false;

@@ -184,6 +184,11 @@ int ggq_decode_plan(int fmt, int64_t O, int64_t T, int64_t K, int* out9);
  * written to out[cap] (NUL-terminated).  0, or GGQ_E_* (<0).  bench.py reports it as `roofline.kernel`. */
 int ggq_describe(int fmt, int64_t O, int64_t T, int64_t K, char* out, int cap);
 
+/* Development aid: `buf` = device buffer of 16 x 320 x 8 uint64 (or NULL to stop).  While set, every decode-family launch
+ * writes per-CTA %globaltimer stamps of its phases (entry, first boxes issued, dependency wait passed, activations
+ * staged, warp 0 done, CTA done) into slot (launch index % 16).  tools/trace_decode.py prints the timeline. */
+void ggq_dev_set_trace(void* buf);
+
 /* Kernels launched by this library since load (all families; for bench.py's `gpu_launches`). */
 int64_t ggq_launch_count(void);
 

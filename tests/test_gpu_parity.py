@@ -234,6 +234,64 @@ def test_real_packer_weights_large_rows_sampled_oracle(ext, fmt):
     assert orc.allclose_ref(Ccpu.astype(np.float32), C[:, rows].astype(np.float32), 0.01)
 
 
+def _gpu_packed(fmt, M, K, seed):
+    """fp32 N(0, 0.02) weights packed on the GPU by the repo's packers (byte-identical to the reference's, see
+    tests/test_gpu_quantize_ops.py), in row chunks that bound the temporary fp32 memory."""
+    from utils.quantize.q4_k import quantize_to_q4_k
+    from utils.quantize.q6_k import quantize_to_q6_k
+    from utils.quantize.q8_0 import quantize_to_q8_0
+    pack = {"q8_0": quantize_to_q8_0, "q4_k": quantize_to_q4_k, "q6_k": quantize_to_q6_k}[fmt]
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(seed)
+    rb = orc.packed_nbytes(fmt, 1, K)
+    out = torch.empty(M * rb, dtype=torch.int8, device="cuda:0")
+    step = max(1, (1 << 27) // K)
+    for r0 in range(0, M, step):
+        r1 = min(M, r0 + step)
+        w = torch.randn((r1 - r0, K), device="cuda:0", dtype=torch.float32, generator=g) * 0.02
+        out[r0 * rb:r1 * rb] = pack(w.half() if fmt == "q8_0" else w)
+    return out
+
+
+def _check_sampled_rows(fmt, Ad, X, M, N, K, C, n_rows, what):
+    """Tier 1 of C[:, rows] for the first / last rows (tile edges) and a random sample (rows are independent)."""
+    rows = np.unique(np.concatenate([np.arange(0, 20), np.arange(M - 20, M),
+                                     np.random.default_rng(5).choice(M, n_rows, replace=False)]))
+    rb = orc.packed_nbytes(fmt, 1, K)
+    idx = torch.from_numpy(rows).to("cuda:0")
+    Asub = Ad.view(M, rb)[idx].cpu().numpy().reshape(-1)
+    got = C[:, idx].cpu().numpy()
+    return check_tier1(fmt, Asub, X, len(rows), N, K, got, what)
+
+
+# every cell of BASELINE.json's metric at its full size (test/test_mmq_q4_k.py:17-40 is the model: packed synthetic
+# weights, fp16 activations, compare with the CPU reference) — the oracle runs on sampled rows
+BASELINE_DECODE = [("q8_0", 28672, 8192), ("q4_k", 128256, 4096), ("q6_k", 128256, 4096), ("q8_0", 4096, 4096),
+                   ("q4_k", 14336, 4096), ("q6_k", 4096, 14336), ("q4_k", 8192, 28672), ("q6_k", 128256, 8192)]
+
+
+@pytest.mark.parametrize("fmt,M,K", BASELINE_DECODE)
+def test_baseline_decode_shapes_full_size(ext, fmt, M, K):
+    Ad = _gpu_packed(fmt, M, K, seed=M % 97)
+    for N in (1, 8, 16):
+        X = rand_x(N, K, 50 + N)
+        C = entry(fmt)(Ad, dev(X), M, N, K)
+        torch.cuda.synchronize()
+        assert C.shape == (N, M)
+        _check_sampled_rows(fmt, Ad, X, M, N, K, C, 64, f"baseline decode T={N}")
+
+
+@pytest.mark.parametrize("fmt,M,K,N", [("q4_k", 28672, 8192, 4096), ("q8_0", 28672, 8192, 4096),
+                                       ("q6_k", 4096, 14336, 2048), ("q6_k", 128256, 4096, 2048)])
+def test_baseline_prefill_shapes_full_size(ext, fmt, M, K, N):
+    Ad = _gpu_packed(fmt, M, K, seed=N % 89)
+    X = rand_x(N, K, 60)
+    C = entry(fmt)(Ad, dev(X), M, N, K)
+    torch.cuda.synchronize()
+    assert ext.lib().ggq_select_family(ext.FMT_ID[fmt], M, N, K) == ext.FAMILY_PREFILL
+    _check_sampled_rows(fmt, Ad, X, M, N, K, C, 24, "baseline prefill")
+
+
 @pytest.mark.parametrize("fmt", FMTS)
 def test_full_size_properties(ext, fmt):
     """BASELINE.json-sized layer (Llama-3-8B, K=4096, O=14336): size-independent properties —
