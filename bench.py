@@ -313,6 +313,48 @@ def prefill_cell(torch, ext, name, fmt, o, k, t, tf_peak, W=None, seed=11):
     return cell
 
 
+def swiglu_cell(torch, ext, name, fmt, o, k, ts, hbm_peak, seed=17):
+    """Fused SwiGLU up-projection (ggq_mm_swiglu): GB/s over the packed bytes of BOTH matrices, next to the two mmq calls
+    + torch silu*mul it replaces.  Parity: sampled rows vs silu(fp16(ref32 gate)) * fp16(ref32 up)."""
+    from kernels.swiglu import mmq_swiglu
+    cells = []
+    nbytes = 2 * packed_bytes(fmt, o, k)
+    copies = max(1, min(32, -(-2 * L2_BYTES // nbytes)))
+    Wg = [make_weights(torch, fmt, o, k, seed)]
+    Wu = [make_weights(torch, fmt, o, k, seed + 1)]
+    Wg += [Wg[0].clone() for _ in range(copies - 1)]
+    Wu += [Wu[0].clone() for _ in range(copies - 1)]
+    pick = sample_rows(o, 96)
+    f = ext.FMT_ID[fmt]
+    for t in ts:
+        X = torch.randn((t, k), device="cuda", dtype=torch.float16)
+        C = mmq_swiglu(fmt, Wg[0], Wu[0], X, o, t, k)
+        torch.cuda.synchronize()
+        x_np = X.cpu().numpy()
+        g = ref_rows(torch, fmt, Wg[0], k, pick, x_np).astype(np.float16).astype(np.float32)
+        u = ref_rows(torch, fmt, Wu[0], k, pick, x_np).astype(np.float16).astype(np.float32)
+        par = parity_of(torch, C, pick, g / (1.0 + np.exp(-g)) * u)
+        n = max(16, copies * 2)
+        gr = graph_of(torch, [lambda i=i: mmq_swiglu(fmt, Wg[i % copies], Wu[i % copies], X, o, t, k) for i in range(n)])
+        ms = timed(torch, None, gr.replay, 5, 3, 1) / n
+
+        def unfused(i):
+            a = ext.mm(f, Wg[i % copies], X, o, t, k)
+            b = ext.mm(f, Wu[i % copies], X, o, t, k)
+            return torch.nn.functional.silu(a) * b
+        gr2 = graph_of(torch, [lambda i=i: unfused(i) for i in range(n)])
+        ms2 = timed(torch, None, gr2.replay, 5, 3, 1) / n
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        cells.append({"cell": f"swiglu {name} T={t}", "family": "decode (fused gate/up + silu*mul)", "fmt": fmt, "O": o, "K": k,
+                      "T": t, "us": round(ms * 1e3, 2), "achieved": round(gbs, 1), "unit": "GB/s", "peak": hbm_peak,
+                      "frac": round(gbs / hbm_peak, 3), "frac_8TBps": round(gbs / 8000.0, 3),
+                      "us_two_mmq_plus_torch_silu_mul": round(ms2 * 1e3, 2), "weight_copies": copies, "parity": par})
+        del gr, gr2
+    del Wg, Wu
+    torch.cuda.empty_cache()
+    return cells
+
+
 def single_gpu_cells(torch, ext, hbm_peak, tf_peak, W_head):
     cells = []
     # BASELINE configs[1] / [2] / [3]: decode, three quant types, M = 1..16
@@ -328,6 +370,9 @@ def single_gpu_cells(torch, ext, hbm_peak, tf_peak, W_head):
     cells.append(prefill_cell(torch, ext, "Q8_0 FFN 28672x8192", "q8_0", 28672, 8192, 4096, tf_peak))
     cells.append(prefill_cell(torch, ext, "Q6_K down_proj 4096x14336", "q6_k", 4096, 14336, 2048, tf_peak))
     cells.append(prefill_cell(torch, ext, "Q6_K lm_head 128256x4096", "q6_k", 128256, 4096, 2048, tf_peak))
+    # the fused SwiGLU up-projection on the Llama-3-8B / 70B FFN shapes
+    cells += swiglu_cell(torch, ext, "Q4_K FFN gate+up 2x14336x4096", "q4_k", 14336, 4096, (1, 8), hbm_peak)
+    cells += swiglu_cell(torch, ext, "Q4_K FFN gate+up 2x28672x8192", "q4_k", 28672, 8192, (1, 8), hbm_peak)
     # configs[4] layers on ONE GPU (the N = 1 point of the N-split cells below)
     cells += decode_cell(torch, ext, "cfg5 Q6_K lm_head 128256x8192", "q6_k", 128256, 8192, (1,), hbm_peak)
     cells += decode_cell(torch, ext, "cfg5 Q4_K FFN up 28672x8192", "q4_k", 28672, 8192, (1,), hbm_peak)
@@ -507,48 +552,38 @@ def run_ours(args):
         launches = (ext.launch_count() - l0) - args.warmup
         ms_k = ms   # the step IS the kernel (one library call per step)
 
-        # e2e: pinned host X in, host C out, every step; copies on a second stream, double-buffered, so the copy of
-        # step i overlaps the kernel of step i+1 and the kernels stay back to back on the compute stream
-        comp = torch.cuda.current_stream()
-        copy = torch.cuda.Stream()
-        ev_x = [torch.cuda.Event() for _ in range(2)]
-        ev_k = [torch.cuda.Event() for _ in range(2)]
+        # e2e: the host-buffer call (kernels.host.HostPipe -> ggq_mm_host): pinned host X in, host C out, every step; the
+        # library runs copy-in / kernel / copy-out on three streams with rotating slots, so the copies of neighbouring
+        # steps overlap the kernel and the kernels stay back to back
+        from kernels.host import HostPipe
+        from kernels import host as _host
+        pipe = HostPipe(FMT, Wc[0], rows, K, max_tokens=T, depth=3)   # (the weights are an argument of every call)
+        mm_host = _host._lib().ggq_mm_host
 
         def step_e2e():
             i = it[0] = it[0] + 1
             b = i & 1
-            with torch.cuda.stream(copy):
-                copy.wait_event(ev_k[b])                         # kernel i-2 has read x_dev[b]
-                x_dev[b].copy_(x_host[b], non_blocking=True)
-                ev_x[b].record(copy)
-            comp.wait_event(ev_x[b])
-            Cb = mmq_q4_k(Wc[b], x_dev[b], rows, T, K)           # the reference-named entry point (allocates its result)
-            ev_k[b].record(comp)
-            Cb.record_stream(copy)
-            with torch.cuda.stream(copy):
-                copy.wait_event(ev_k[b])
-                c_host[b].copy_(Cb, non_blocking=True)
-
-        def e2e_region(n):
-            for _ in range(n):
-                step_e2e()
-            comp.wait_stream(copy)   # the timed region ends when the last result is on the host
+            rc = mm_host(pipe._h, f, Wc[b].data_ptr(), x_host[b].data_ptr(), c_host[b].data_ptr(), rows, T, K)
+            assert rc == 0, rc
 
         def timed_e2e(steps, warmup):
-            e2e_region(warmup)
+            for _ in range(warmup):
+                step_e2e()
+            pipe.sync()
             torch.cuda.synchronize()
+            s_in, s_out = pipe.stream(0), pipe.stream(2)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            e2e_region(steps)
-            e1.record()
+            e0.record(s_in)            # the first copy-in of the region follows on this stream
+            for _ in range(steps):
+                step_e2e()
+            e1.record(s_out)           # after the last copy-out
+            pipe.sync()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / steps
         ms_e2e = timed_e2e(args.steps, args.warmup)
-        torch.cuda.synchronize()
         e2e_par = parity_of(torch, c_host[it[0] & 1].to("cuda"), pick,
                             ref_rows(torch, FMT, W, K, pick, x_host[it[0] & 1].numpy()))
         assert e2e_par["ok"], ("e2e parity", e2e_par)
-
         # latency form: the public entry point, one step at a time, host synchronisation after every step
         def step_sync():
             x_dev[0].copy_(x_host[0], non_blocking=True)
@@ -586,7 +621,8 @@ def run_ours(args):
                "fmt": FMT, "O": O, "K": K, "T": T}
         e2e = {"value": total_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": T * K * 2, "d2h_bytes_per_step": T * O * 2,
-               "mode": "throughput: pinned H2D of X and D2H of C every step on a copy stream, double-buffered; ext.mm on the compute stream",
+               "mode": "throughput: ggq_mm_host (kernels.host.HostPipe) per step — pinned H2D of X, kernel, D2H of C on the "
+                       "library's three streams with rotating slots; timed with CUDA events from the first copy-in to the last copy-out",
                "latency_ms_per_step_synchronised": ms_lat, "parity": e2e_par}
         extra_cells = []
     else:

@@ -1,4 +1,5 @@
 // api.cu — the extern "C" boundary of libggq.so (include/ggq.h): validation + family dispatch.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -99,6 +100,28 @@ static int mm(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
     return GGQ_E_FAMILY;
 }
 
+// C = silu(G) * C elementwise over [T, O] fp16 (the composed form of ggq_mm_swiglu: G = gate projection, C = up projection)
+__global__ void silu_mul_kernel(const __half* __restrict__ G, __half* C, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float g = __half2float(G[i]), u = __half2float(C[i]);
+        C[i] = __float2half_rn(g / (1.f + __expf(-g)) * u);
+    }
+}
+
+static MmArgs placeholder_args(int64_t O, int64_t T, int64_t K) {
+    MmArgs a{};
+    a.W = reinterpret_cast<const uint8_t*>(uintptr_t{256});  // alignment-neutral placeholders (host-side planning only)
+    a.X = reinterpret_cast<const void*>(uintptr_t{256});
+    a.n_out = 1;
+    a.ldx = K;
+    a.ldc = O;
+    a.O = O;
+    a.T = T;
+    a.K = K;
+    return a;
+}
+
 static int dequant(int fmt, const void* W, void* out, int64_t O, int64_t K, void* stream) {
     if (O < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
     if (O == 0 || K == 0) return 0;
@@ -129,6 +152,49 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
               int64_t T, int64_t K, int family, void* stream) {
     if (family < GGQ_FAMILY_AUTO || family > GGQ_FAMILY_SKINNY) return GGQ_E_FAMILY;
     return mm(fmt, W, X, ldx, C_out, n_out, ldc, O, T, K, family, stream);
+}
+
+int64_t ggq_mm_swiglu_workspace(int fmt, int64_t O, int64_t T, int64_t K) {
+    if (fmt < GGQ_Q8_0 || fmt > GGQ_Q6_K) return GGQ_E_FORMAT;
+    if (O < 0 || T < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    if (O == 0 || T == 0 || K == 0) return 0;
+    MmArgs a = placeholder_args(O, T, K);
+    a.W2 = a.W;
+    return launch_decode_dual(fmt, a, true) == 0 ? 0 : T * O * 2;
+}
+
+int ggq_mm_swiglu(int fmt, const void* Wg, const void* Wu, const void* X, void* C, int64_t O, int64_t T, int64_t K,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+    void* outs[1] = {C};
+    int v = validate(fmt, Wg, X, outs, 1, K, O, O, T, K);
+    if (v != 0) return v;
+    if (O == 0 || T == 0) return 0;
+    if (K > 0 && !Wu) return GGQ_E_POINTER;
+    if (K == 0) return mm(fmt, Wg, X, K, outs, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);  // silu(0) * 0 = 0
+    MmArgs a = placeholder_args(O, T, K);
+    a.W = static_cast<const uint8_t*>(Wg);
+    a.W2 = static_cast<const uint8_t*>(Wu);
+    a.X = X;
+    a.C[0] = C;
+    a.stream = static_cast<cudaStream_t>(stream);
+    static const bool no_fused = getenv("GGQ_SWIGLU_COMPOSED") != nullptr;   // dev: always take the composed form
+    if (!no_fused) {
+        v = launch_decode_dual(fmt, a, false);
+        if (v != GGQ_E_FAMILY) return v;
+    }
+    // composed: gate projection into the workspace, up projection into C, one elementwise pass
+    if (!workspace) return GGQ_E_POINTER;
+    if (workspace_bytes < T * O * 2) return GGQ_E_SHAPE;
+    void* ws[1] = {workspace};
+    v = mm(fmt, Wg, X, K, ws, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);
+    if (v != 0) return v;
+    v = mm(fmt, Wu, X, K, outs, 1, O, O, T, K, GGQ_FAMILY_AUTO, stream);
+    if (v != 0) return v;
+    const int64_t n = T * O;
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(num_sms()) * 8));
+    silu_mul_kernel<<<blocks, 256, 0, a.stream>>>(static_cast<const __half*>(workspace), static_cast<__half*>(C), n);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
 }
 
 int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* C, int64_t ldc, int64_t O, int64_t T, int64_t K,

@@ -34,6 +34,7 @@ struct MmArgs {
     cudaStream_t stream;
     const PeerSync* sync;  // decode family only; nullptr = plain call
     int* ctas_out;
+    const uint8_t* W2;     // fused SwiGLU (launch_decode_dual): the up matrix, W is the gate matrix; else nullptr
 };
 
 // Output pointers passed to kernels by value.  n > 1 = the same tile is also stored to peer-mapped
@@ -55,6 +56,7 @@ int num_sms();  // SM count of the current device (cached per device)
 // families (one launcher per translation unit); return cudaError_t / GGQ_E_*
 int launch_generic(int fmt, const MmArgs& a);
 int launch_decode(int fmt, const MmArgs& a);
+int launch_decode_dual(int fmt, const MmArgs& a, bool plan_only);  // decode_dual.cu; GGQ_E_FAMILY = no fused plan
 int launch_prefill(int fmt, const MmArgs& a);
 int launch_skinny(int fmt, const MmArgs& a);
 bool decode_supports(int fmt, const MmArgs& a);

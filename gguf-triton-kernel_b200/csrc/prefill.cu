@@ -257,7 +257,10 @@ prefill2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (use > 0) mbar_wait(&free_[s], (use - 1) & 1u);
             uint4 v[8];
             const int off = (col * U::UNIT_BYTES) & 15;
-            dequant64(U{}, units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
+            if constexpr (FMT == 2)   // conflict-free 128-bit loads + register realignment (same arithmetic as dequant64)
+                dequant_q6_k_sm<2>(units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
+            else
+                dequant64(U{}, units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
             uint8_t* brow = stages + s * STAGE2_BYTES + A2_BYTES + (urow >> 3) * 1024 + (urow & 7) * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(j) ^ sw) << 4)) = v[j];
@@ -328,7 +331,8 @@ static int launch_t(const MmArgs& a) {
     if (!make_map_2d(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.X, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.T),
                      static_cast<uint64_t>(a.ldx) * 2, BK, 128, CU_TENSOR_MAP_SWIZZLE_128B))
         return static_cast<int>(cudaErrorInvalidValue);
-    // W: the packed rows viewed as int32 [O, rowB/4], box BOX_BYTES/4 x 128 rows; rows >= O are zero-filled
+    // W: the packed rows viewed as int32 [O, rowB/4], box BOX_BYTES/4 x 128 rows; rows >= O and bytes past the end of a row
+    // are zero-filled
     if (!make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_INT32, a.W, static_cast<uint64_t>(rowB / 4), static_cast<uint64_t>(a.O),
                      static_cast<uint64_t>(rowB), U::BOX_BYTES / 4, UNIT_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE))
         return static_cast<int>(cudaErrorInvalidValue);

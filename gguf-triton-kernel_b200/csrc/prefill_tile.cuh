@@ -28,8 +28,9 @@ template <> struct Unit<0> {  // Q8_0: 4 blocks = 128 weights = 136 B; block col
 template <> struct Unit<1> {  // Q4_K: 1 super-block = 256 weights = 144 B, always 16-byte aligned
     static constexpr int QK = 256, BLK = 144, UNIT_K = 256, UNIT_BYTES = 144, BOX_BYTES = 144;
 };
-template <> struct Unit<2> {  // Q6_K: 1 super-block = 256 weights = 210 B at 210c (even offsets 0..14 mod 16)
-    static constexpr int QK = 256, BLK = 210, UNIT_K = 256, UNIT_BYTES = 210, BOX_BYTES = 224;
+template <> struct Unit<2> {  // Q6_K: 1 super-block = 256 weights = 210 B at 210c (even offsets 0..14 mod 16); the box is
+                              // 240 B = an odd number of 16-byte vectors per row (dequant_q6_k_sm)
+    static constexpr int QK = 256, BLK = 210, UNIT_K = 256, UNIT_BYTES = 210, BOX_BYTES = 240;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -185,23 +186,19 @@ template <bool ODD> __device__ __forceinline__ void ld8w(const uint8_t* p, uint3
     }
 }
 
-template <int HALF, bool ODD>
-__device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4* out) {
-    const int h = kb >> 1, gp = kb & 1;
-    const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
-    const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
+// The arithmetic, shared by every loader: lw[8 gi + i] = the 32 ql bytes of group g = 2gp + gi, hw = the 32 qh bytes of
+// half h, scw = the int8 scales of sub-blocks 8h + 4gp + 0..3, d = the block scale.
+template <int HALF>
+__device__ __forceinline__ void dequant_q6_k_core(const uint32_t (&lw)[16], const uint32_t (&hw)[8], uint32_t scw, float d, int gp,
+                                                  uint4* out) {
     float ds[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         ds[i] = d * static_cast<float>(static_cast<int>(static_cast<int8_t>((scw >> (8 * i)) & 0xffu)));  // exact
-    uint32_t hw[8];
-    ld8w<ODD>(b + 128 + 32 * h, hw);
     const f2 m32{-8388640.f, -8388640.f};  // -(2^23 + 32): (2^23 + q) + this == q - 32 exactly
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {  // group g = 2gp + gi
         if (HALF != 2 && HALF != gi) continue;
-        uint32_t lw[8];
-        ld8w<ODD>(b + 64 * h + 32 * gi, lw);
         // the 2 qh bits of group g sit at bits 2g, 2g+1 of every byte: rotate them to bits 4, 5 (no bits of a
         // neighbouring byte can reach positions 4, 5: the rotation is by -4, -2, 0 or +2)
         const uint32_t rot = static_cast<uint32_t>(4 * gp + 2 * gi - 4) & 31u;
@@ -213,7 +210,7 @@ __device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4*
             uint32_t r[4];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
-                const uint32_t lo = (lw[2 * c4 + v] >> (4 * gp)) & 0x0F0F0F0Fu;
+                const uint32_t lo = (lw[8 * gi + 2 * c4 + v] >> (4 * gp)) & 0x0F0F0F0Fu;
                 const uint32_t hr = __funnelshift_r(hw[2 * c4 + v], hw[2 * c4 + v], rot);
                 const uint32_t q = (hr & 0x30303030u) | lo;  // four 6-bit quants
                 const f2 a = mul2(s2, add2(magic2(q, 0), m32)), c = mul2(s2, add2(magic2(q, 2), m32));
@@ -223,6 +220,74 @@ __device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4*
             o[c4] = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
+}
+
+// loader 1: block at a 2-byte aligned address (global memory / the 16-byte aligned supersets of the decode family)
+template <int HALF, bool ODD>
+__device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4* out) {
+    const int h = kb >> 1, gp = kb & 1;
+    const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
+    const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
+    uint32_t hw[8], lw[16];
+    ld8w<ODD>(b + 128 + 32 * h, hw);
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+        if (HALF != 2 && HALF != gi) continue;
+        uint32_t t[8];
+        ld8w<ODD>(b + 64 * h + 32 * gi, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lw[8 * gi + i] = t[i];
+    }
+    dequant_q6_k_core<HALF>(lw, hw, scw, d, gp, out);
+}
+
+// loader 2 (shared memory, thread = row): `row16` = 16-byte aligned start of the row's staged bytes, the block begins `off`
+// bytes in (even, 0..14, the same for every row of a block column, so the switch below is warp-uniform).  TMA can only
+// start a box at a 16-byte aligned global address (an element-granular start faults: tools/probes/tma_probe.cu), so the
+// block cannot be staged aligned.  With loader 1 the 32-bit loads of the 32 rows, a multiple of 16 bytes apart, fall into
+// 4 or 8 banks: 4- to 8-way conflicts made the shared-memory pipe the bound of the Q6_K prefill and skinny kernels.
+// Here the row pitch is an ODD multiple of 16 bytes (Q6K_ROW_PITCH) and every load is a 128-bit load of an aligned
+// vector — conflict free with thread = row — and the words are shifted into place in registers.
+constexpr int Q6K_ROW_PITCH = 240;
+template <int WS, bool ODD>   // off = 4 WS + (ODD ? 2 : 0)
+__device__ __forceinline__ void q6k_gather(const uint4* ql, const uint4* qh, uint32_t (&lw)[16], uint32_t (&hw)[8]) {
+    constexpr int NL = (WS == 0 && !ODD) ? 4 : 5, NH = (WS == 0 && !ODD) ? 2 : 3;
+    uint32_t a[20], c[12];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const uint4 v = ql[i];
+        a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+        const uint4 v = qh[i];
+        c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lw[i] = ODD ? __funnelshift_r(a[WS + i], a[WS + i + 1], 16) : a[WS + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hw[i] = ODD ? __funnelshift_r(c[WS + i], c[WS + i + 1], 16) : c[WS + i];
+}
+template <int HALF>
+__device__ __forceinline__ void dequant_q6_k_sm(const uint8_t* row16, int off, int kb, uint4* out) {
+    const int h = kb >> 1, gp = kb & 1;
+    const uint8_t* b = row16 + off;
+    const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
+    const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);
+    const uint4* ql = reinterpret_cast<const uint4*>(row16 + 64 * h);
+    const uint4* qh = reinterpret_cast<const uint4*>(row16 + 128 + 32 * h);
+    uint32_t lw[16], hw[8];
+    switch (off >> 1) {
+        case 0: q6k_gather<0, false>(ql, qh, lw, hw); break;
+        case 1: q6k_gather<0, true>(ql, qh, lw, hw); break;
+        case 2: q6k_gather<1, false>(ql, qh, lw, hw); break;
+        case 3: q6k_gather<1, true>(ql, qh, lw, hw); break;
+        case 4: q6k_gather<2, false>(ql, qh, lw, hw); break;
+        case 5: q6k_gather<2, true>(ql, qh, lw, hw); break;
+        case 6: q6k_gather<3, false>(ql, qh, lw, hw); break;
+        default: q6k_gather<3, true>(ql, qh, lw, hw); break;
+    }
+    dequant_q6_k_core<HALF>(lw, hw, scw, d, gp, out);
 }
 
 template <int HALF>

@@ -66,23 +66,17 @@ __device__ __forceinline__ void dq64_q4_k(const uint8_t* p, int kb, uint4 (&out)
     }
 }
 
-// ---- Q6_K: kb = 0..3 (half h = kb >> 1, groups 2gp, 2gp+1 with gp = kb & 1), see prefill_tile.cuh dequant_q6_k_al ----
-template <bool ODD>
-__device__ __forceinline__ void dq64_q6_k_al(const uint8_t* b, int kb, uint4 (&out)[8]) {
-    const int h = kb >> 1, gp = kb & 1;
-    const float d = pre::hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
-    const uint32_t scw = pre::ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
+// ---- Q6_K: kb = 0..3 (half h = kb >> 1, groups 2gp, 2gp+1 with gp = kb & 1), see prefill_tile.cuh dequant_q6_k_core ----
+// lw[8 gi + i] = the 32 ql bytes of group 2gp + gi, hw = the 32 qh bytes of half h, scw = 4 int8 scales, d = block scale
+__device__ __forceinline__ void dq64_q6_k_core(const uint32_t (&lw)[16], const uint32_t (&hw)[8], uint32_t scw, float d, int gp,
+                                               uint4 (&out)[8]) {
     __half2 a2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         a2[i] = __float2half2_rn(d * static_cast<float>(static_cast<int>(static_cast<int8_t>((scw >> (8 * i)) & 0xffu))));
-    uint32_t hw[8];
-    pre::ld8w<ODD>(b + 128 + 32 * h, hw);
     const __half2 bias = __float2half2_rn(1056.f);  // (1024 + q) - 1056 = q - 32, exact
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {  // group g = 2gp + gi
-        uint32_t lw[8];
-        pre::ld8w<ODD>(b + 64 * h + 32 * gi, lw);
         const uint32_t rot = static_cast<uint32_t>(4 * gp + 2 * gi - 4) & 31u;
         uint4* o = out + 4 * gi;
 #pragma unroll
@@ -91,7 +85,7 @@ __device__ __forceinline__ void dq64_q6_k_al(const uint8_t* b, int kb, uint4 (&o
             uint32_t r[4];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
-                const uint32_t lo = (lw[2 * c4 + v] >> (4 * gp)) & 0x0F0F0F0Fu;
+                const uint32_t lo = (lw[8 * gi + 2 * c4 + v] >> (4 * gp)) & 0x0F0F0F0Fu;
                 const uint32_t hr = __funnelshift_r(hw[2 * c4 + v], hw[2 * c4 + v], rot);
                 const uint32_t q = (hr & 0x30303030u) | lo;  // four 6-bit quants
                 r[2 * v] = h2u(__hmul2(__hsub2(u2h(__byte_perm(q, 0x64646464u, 0x4140)), bias), s2));
@@ -100,6 +94,44 @@ __device__ __forceinline__ void dq64_q6_k_al(const uint8_t* b, int kb, uint4 (&o
             o[c4] = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
+}
+// block at a 2-byte aligned address (GGQ_SKINNY_EXACT builds and tests of the arithmetic)
+template <bool ODD>
+__device__ __forceinline__ void dq64_q6_k_al(const uint8_t* b, int kb, uint4 (&out)[8]) {
+    const int h = kb >> 1, gp = kb & 1;
+    const float d = pre::hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
+    const uint32_t scw = pre::ld32_any(b + 192 + 8 * h + 4 * gp);  // scales of sub-blocks 8h + 4gp + 0..3
+    uint32_t hw[8], lw[16], t[8];
+    pre::ld8w<ODD>(b + 128 + 32 * h, hw);
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+        pre::ld8w<ODD>(b + 64 * h + 32 * gi, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lw[8 * gi + i] = t[i];
+    }
+    dq64_q6_k_core(lw, hw, scw, d, gp, out);
+}
+// shared memory, thread = row: conflict-free 128-bit loads of aligned vectors + register realignment (prefill_tile.cuh
+// dequant_q6_k_sm has the full story).  row16 is 16-byte aligned, the block begins `off` bytes in (even, warp-uniform).
+__device__ __forceinline__ void dq64_q6_k_sm(const uint8_t* row16, int off, int kb, uint4 (&out)[8]) {
+    const int h = kb >> 1, gp = kb & 1;
+    const uint8_t* b = row16 + off;
+    const float d = pre::hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
+    const uint32_t scw = pre::ld32_any(b + 192 + 8 * h + 4 * gp);
+    const uint4* ql = reinterpret_cast<const uint4*>(row16 + 64 * h);
+    const uint4* qh = reinterpret_cast<const uint4*>(row16 + 128 + 32 * h);
+    uint32_t lw[16], hw[8];
+    switch (off >> 1) {
+        case 0: pre::q6k_gather<0, false>(ql, qh, lw, hw); break;
+        case 1: pre::q6k_gather<0, true>(ql, qh, lw, hw); break;
+        case 2: pre::q6k_gather<1, false>(ql, qh, lw, hw); break;
+        case 3: pre::q6k_gather<1, true>(ql, qh, lw, hw); break;
+        case 4: pre::q6k_gather<2, false>(ql, qh, lw, hw); break;
+        case 5: pre::q6k_gather<2, true>(ql, qh, lw, hw); break;
+        case 6: pre::q6k_gather<3, false>(ql, qh, lw, hw); break;
+        default: pre::q6k_gather<3, true>(ql, qh, lw, hw); break;
+    }
+    dq64_q6_k_core(lw, hw, scw, d, gp, out);
 }
 
 // p: 16-byte aligned superset of the block column in this row; off: byte offset of the block inside it
@@ -113,9 +145,7 @@ __device__ __forceinline__ void dq64(const uint8_t* p, int off, int kb, uint4 (&
     } else if constexpr (FMT == 1) {
         dq64_q4_k(p, kb, out);
     } else {
-        const uint8_t* b = p + off;
-        if (off & 2) dq64_q6_k_al<true>(b, kb, out);
-        else dq64_q6_k_al<false>(b, kb, out);
+        dq64_q6_k_sm(p + (off & ~15), off & 15, kb, out);
     }
 #endif
 }

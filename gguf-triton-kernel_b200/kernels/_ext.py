@@ -1,7 +1,10 @@
-"""Loader + thin ctypes binding of libggq.so (the C ABI in include/ggq.h).
+"""Loader + bindings of libggq.so (the C ABI in include/ggq.h).
 
-There is NO fallback: if the library is missing or a call fails, the op raises.  torch is used only
-for device memory, the current stream and the device guard — the arithmetic is all in libggq.so.
+Two bindings of the same C ABI: the per-step calls (`mm`, `mm_swiglu`) go through the PyTorch extension
+`_ggq_torch.so` (csrc/torch_binding.cpp: operand checks, result allocation, current stream, ~2 us of host time per
+call); everything else (queries, packers, dequantizers, the multi-GPU and host-pipe calls) through ctypes.
+There is NO fallback: if a library is missing or a call fails, the op raises.  torch is used only for device
+memory, the current stream and the device guard — the arithmetic is all in libggq.so.
 """
 from __future__ import annotations
 
@@ -13,6 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB_PATH = os.path.join(_PKG, "libggq.so")
 _lib = None
+_text = None
 
 GGQ_Q8_0, GGQ_Q4_K, GGQ_Q6_K = 0, 1, 2
 FAMILY_AUTO, FAMILY_GENERIC, FAMILY_DECODE, FAMILY_PREFILL, FAMILY_SKINNY = 0, 1, 2, 3, 4
@@ -55,6 +59,25 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def torch_ext():
+    """The PyTorch extension module (`_ggq_torch`), loaded from the package directory; raises when it is not built."""
+    global _text
+    if _text is None:
+        lib()   # libggq.so first: the extension links it by name
+        path = os.path.join(_PKG, "_ggq_torch.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not found — the PyTorch extension is not built. Run `make -C {_PKG}`. "
+                               "There is no fallback binding for the per-step calls.")
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ggq_torch", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if mod.version() != lib().ggq_version():
+            raise RuntimeError("_ggq_torch.so and libggq.so were built from different sources; rebuild")
+        _text = mod
+    return _text
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {lib().ggq_error_string(rc).decode()}")
@@ -88,30 +111,27 @@ def _current_stream(index: int) -> int:
 def mm(fmt: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, family: int = FAMILY_AUTO,
        out: torch.Tensor | None = None) -> torch.Tensor:
     """C[N, M] (fp16) = B[N, K] @ dequant(A)[M, K]^T on A's device, current stream, asynchronous."""
+    return torch_ext().mm(fmt, A, B, M, N, K, family, out)
+
+
+def mm_ctypes(fmt: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, family: int = FAMILY_AUTO,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """The same call through the ctypes binding (tests: both bindings reach the same C entry point)."""
     _check_operands(fmt, A, B, M, N, K)
     C = torch.empty((N, M), device=A.device, dtype=torch.float16) if out is None else out
     if out is not None and (out.dtype != torch.float16 or out.shape != (N, M) or not out.is_contiguous()
                             or out.device != A.device):
         raise ValueError("out must be a contiguous float16 [N, M] tensor on A's device")
-    index = A.device.index
-    L = lib()
-
-    def launch() -> int:
-        stream = _current_stream(index)
-        if family == FAMILY_AUTO:
-            fn = (L.ggq_mm_q8_0_f16, L.ggq_mm_q4_k_f16, L.ggq_mm_q6_k_f16)[fmt]
-            return fn(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, stream)
-        outs = (_P * 1)(C.data_ptr())
-        return L.ggq_mm_ex(fmt, A.data_ptr(), B.data_ptr(), K, outs, 1, M, M, N, K, family, stream)
-
-    if torch.cuda.current_device() == index:   # the common case: no device switch (the guard costs microseconds)
-        rc = launch()
-    else:
-        with torch.cuda.device(index):
-            rc = launch()
-    if rc != 0:
-        check(rc, "ggq_mm")
+    outs = (_P * 1)(C.data_ptr())
+    with torch.cuda.device(A.device):
+        rc = lib().ggq_mm_ex(fmt, A.data_ptr(), B.data_ptr(), K, outs, 1, M, M, N, K, family, _current_stream(A.device.index))
+    check(rc, "ggq_mm")
     return C
+
+
+def mm_swiglu(fmt: int, Ag: torch.Tensor, Au: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    """C[N, M] (fp16) = silu(B @ dequant(Ag)^T) * (B @ dequant(Au)^T)  (ggq_mm_swiglu, include/ggq.h)."""
+    return torch_ext().mm_swiglu(fmt, Ag, Au, B, M, N, K)
 
 
 def mm_ex(fmt: int, A: torch.Tensor, B: torch.Tensor, outs: list[int], ldc: int, M: int, N: int, K: int, *,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GGQ_VERSION 107 /* 0.1.7 */
+#define GGQ_VERSION 108 /* 0.1.8 */
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define GGQ_E_SHAPE     (-1) /* K not a multiple of the block size (the reference's only assert:   */
@@ -80,6 +80,20 @@ int ggq_mm_q6_k_f16(const void* W, const void* X, void* C, int64_t O, int64_t T,
  */
 int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C_out, int n_out, int64_t ldc,
               int64_t O, int64_t T, int64_t K, int family, void* stream);
+
+/*
+ * Fused SwiGLU up-projection, the step that follows the gate/up matmuls of a Llama FFN (the reference has
+ * no counterpart: its callers run mmq twice and apply silu(gate) * up in torch):
+ *     C[T, O] = silu(G) * U,   G = fp16(X . dequant(Wg)^T),  U = fp16(X . dequant(Wu)^T),  silu and product in fp32
+ * i.e. exactly what `F.silu(mmq(Wg, X).float()) * mmq(Wu, X).float()` rounded to fp16 gives.  Wg / Wu: packed [O, K] of the
+ * same format.  T <= 16 on decode-eligible shapes: ONE kernel streams both matrices once and applies the activation in
+ * the accumulator registers (no intermediate [T, 2*O] in HBM).  Other shapes: gate GEMM -> workspace, up GEMM -> C,
+ * one elementwise pass; that form needs `workspace_bytes` >= ggq_mm_swiglu_workspace(...) (0 when the fused kernel
+ * runs; `workspace` may then be NULL).
+ */
+int64_t ggq_mm_swiglu_workspace(int fmt, int64_t O, int64_t T, int64_t K);
+int ggq_mm_swiglu(int fmt, const void* Wg, const void* Wu, const void* X, void* C, int64_t O, int64_t T, int64_t K,
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Decode-family GEMV/skinny GEMM with the N-split exchange fused INTO the kernel (T <= 8, T*K <= 65536):
@@ -133,6 +147,28 @@ typedef struct ggq_peer_sync {
 /* Returns 0 and writes the number of CTAs launched to *ctas_out. */
 int ggq_mm_sync(int fmt, const void* W, const void* X, int64_t ldx, void* C, int64_t ldc, int64_t O, int64_t T, int64_t K,
                 const ggq_peer_sync* sync, int* ctas_out, void* stream);
+
+/*
+ * The whole step with HOST activations and a HOST result: what a caller of kernels/mmq_q4_k.py:240 does around the call
+ * (`.cuda()` of the activations, `.cpu()` of the product) behind one C call.  A pipe owns `depth` device slots (X and C
+ * staging buffers, allocated once by ggq_host_pipe_create on the current device — the ONLY functions of this library
+ * that allocate) and three streams: H2D of step i+1 and D2H of step i-1 overlap the kernel of step i.
+ *   W_dev    packed weights on the pipe's device (resident state of the layer, as in the reference)
+ *   X_host   fp16 [T, K] in host memory (page-locked memory makes the copy asynchronous); must stay valid and unchanged
+ *            until the step has been copied in — at the latest after ggq_host_pipe_sync
+ *   C_host   fp16 [T, O] in host memory, complete after ggq_host_pipe_sync (or once `depth` later calls have returned
+ *            and been synchronised by the caller's own means: see ggq_host_pipe_stream)
+ * T*K*2 <= max_x_bytes and T*O*2 <= max_c_bytes, else GGQ_E_SHAPE.  Calls on one pipe must come from one thread at a time.
+ */
+#define GGQ_HOST_PIPE_MAX_DEPTH 8
+typedef struct ggq_host_pipe ggq_host_pipe;
+int ggq_host_pipe_create(ggq_host_pipe** out, int64_t max_x_bytes, int64_t max_c_bytes, int depth);
+int ggq_mm_host(ggq_host_pipe* pipe, int fmt, const void* W_dev, const void* X_host, void* C_host, int64_t O, int64_t T,
+                int64_t K);
+int ggq_host_pipe_sync(ggq_host_pipe* pipe);
+/* cudaStream_t of the pipe: which = 0 copy-in, 1 kernels, 2 copy-out (e.g. to record the caller's own events) */
+void* ggq_host_pipe_stream(ggq_host_pipe* pipe, int which);
+void ggq_host_pipe_destroy(ggq_host_pipe* pipe);
 
 /*
  * Dequantize packed rows to fp16 [O, K] with the SAME device functions the prefill GEMM uses.

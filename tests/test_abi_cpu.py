@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_host_queries():
     from kernels import _ext
     L = _ext.lib()
-    assert L.ggq_version() == 107
+    assert L.ggq_version() == 108
     assert L.ggq_packed_nbytes(0, 4096, 4096) == 17825792          # BASELINE config 1
     assert L.ggq_packed_nbytes(1, 128256, 4096) == 295501824       # config 2
     assert L.ggq_packed_nbytes(2, 4096, 14336) == 48168960         # config 3
@@ -110,3 +110,52 @@ def test_decode_planner_invariants():
             assert slices == 1 and at == 1, (f, o, t, k, list(out))   # every T <= 8 shape of BASELINE configs[1] is unsliced
     out = (ctypes.c_int * 9)()
     assert L.ggq_decode_plan(1, 128256, 1, 4096, out) == 0 and out[5] >= 3   # headline: >= 3 ring stages per warp
+
+
+def test_swiglu_and_host_pipe_argument_errors():
+    """ggq_mm_swiglu / ggq_mm_host validate before anything is enqueued; the workspace query is pure host code."""
+    from kernels import _ext
+    L = _ext.lib()
+    I64, P, INT = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+    L.ggq_mm_swiglu_workspace.argtypes = [INT, I64, I64, I64]
+    L.ggq_mm_swiglu_workspace.restype = I64
+    L.ggq_mm_swiglu.argtypes = [INT, P, P, P, P, I64, I64, I64, P, I64, P]
+    L.ggq_mm_swiglu.restype = INT
+    # decode-sized token counts on 16-byte-aligned rows run the fused kernel: no workspace
+    for f, o, k in ((0, 14336, 4096), (1, 14336, 4096), (2, 14336, 4096), (1, 28672, 8192), (1, 1004, 2048)):
+        for t in (1, 5, 8, 16):
+            assert L.ggq_mm_swiglu_workspace(f, o, t, k) == 0, (f, o, t, k)
+    assert L.ggq_mm_swiglu_workspace(1, 14336, 17, 4096) == 17 * 14336 * 2     # composed form: the gate projection
+    assert L.ggq_mm_swiglu_workspace(1, 14336, 512, 4096) == 512 * 14336 * 2
+    assert L.ggq_mm_swiglu_workspace(1, 14336, 1, 100) == -1 and L.ggq_mm_swiglu_workspace(5, 1, 1, 256) == -4
+    one = ctypes.c_void_p(256)
+    assert L.ggq_mm_swiglu(1, one, one, one, one, 64, 1, 100, None, 0, None) == -1     # K % 256
+    assert L.ggq_mm_swiglu(1, one, None, one, one, 64, 1, 256, None, 0, None) == -2    # no up matrix
+    assert L.ggq_mm_swiglu(1, None, None, None, None, 0, 1, 256, None, 0, None) == 0   # empty problem
+    assert L.ggq_mm_swiglu(1, one, one, one, one, 64, 64, 256, None, 0, None) == -2    # composed form without a workspace
+    from kernels import host
+    H = host._lib()
+    h = ctypes.c_void_p()
+    assert H.ggq_host_pipe_create(ctypes.byref(h), 0, 16, 2) == -1
+    assert H.ggq_host_pipe_create(ctypes.byref(h), 16, 16, 9) == -1
+    assert H.ggq_host_pipe_create(None, 16, 16, 2) == -2
+    assert H.ggq_mm_host(None, 1, one, one, one, 4, 1, 256) == -2
+    assert H.ggq_host_pipe_sync(None) == -2
+
+
+def test_torch_extension_loads_and_checks_operands():
+    """The PyTorch extension is the binding of the per-step calls; its operand checks raise the reference-style errors."""
+    from kernels import _ext
+    from kernels.swiglu import mmq_q4_k_swiglu
+    t = _ext.torch_ext()
+    assert t.version() == _ext.lib().ggq_version()
+    A = torch.zeros(144, dtype=torch.int8)
+    B = torch.zeros((1, 256), dtype=torch.float16)
+    with pytest.raises(ValueError):
+        t.mm(1, A, B, 1, 1, 256)                      # CPU tensors
+    with pytest.raises(TypeError):
+        t.mm(1, A.float(), B, 1, 1, 256)
+    with pytest.raises(ValueError):
+        mmq_q4_k_swiglu(A, A, B, 1, 1, 256)
+    with pytest.raises(AssertionError):
+        mmq_q4_k_swiglu(A, A, B, 1, 1, 100)
