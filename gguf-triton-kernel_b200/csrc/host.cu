@@ -119,6 +119,22 @@ int ggq_host_pipe_sync(ggq_host_pipe* p) {
     return static_cast<int>(e);
 }
 
+int ggq_push_columns(const void* src, void* const* dst, int n_dst, int64_t pitch_bytes, int64_t width_bytes, int64_t rows,
+                     void* stream) {
+    if (n_dst < 0 || n_dst > 8 || pitch_bytes < width_bytes || width_bytes < 0 || rows < 0) return GGQ_E_SHAPE;
+    if (n_dst == 0 || width_bytes == 0 || rows == 0) return 0;
+    if (!src || !dst) return GGQ_E_POINTER;
+    for (int i = 0; i < n_dst; ++i)
+        if (!dst[i]) return GGQ_E_POINTER;
+    for (int i = 0; i < n_dst; ++i) {
+        const cudaError_t e = cudaMemcpy2DAsync(dst[i], static_cast<size_t>(pitch_bytes), src, static_cast<size_t>(pitch_bytes),
+                                                static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyDeviceToDevice,
+                                                static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return 0;
+}
+
 void* ggq_host_pipe_stream(ggq_host_pipe* p, int which) {
     if (!p) return nullptr;
     return which == 0 ? p->s_in : which == 1 ? p->s_mm : which == 2 ? p->s_out : nullptr;

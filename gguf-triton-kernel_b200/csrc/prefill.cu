@@ -259,6 +259,8 @@ prefill2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int off = (col * U::UNIT_BYTES) & 15;
             if constexpr (FMT == 2)   // conflict-free 128-bit loads + register realignment (same arithmetic as dequant64)
                 dequant_q6_k_sm<2>(units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
+            else if constexpr (FMT == 0)
+                dequant_q8_0_sm<2>(units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
             else
                 dequant64(U{}, units + slot * R::UNIT_BYTES + urow * U::BOX_BYTES, off, kin, v);
             uint8_t* brow = stages + s * STAGE2_BYTES + A2_BYTES + (urow >> 3) * 1024 + (urow & 7) * 128;

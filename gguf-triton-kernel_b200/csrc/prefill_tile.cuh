@@ -83,10 +83,10 @@ __device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
 // weights into out[0..3] (the 2-CTA prefill kernel splits a row's k-block over two threads).
 
 // ---- Q8_0 -------------------------------------------------------------------------------------
-// kb: which 64-weight half of the 128-weight unit (blocks 2kb, 2kb+1)
+// The arithmetic on the 17 words of two consecutive blocks (68 bytes from a 4-byte aligned start): w[0] = {d_A, q0 q1},
+// w[8] = {q30 q31 of A, d_B}, w[9..16] = the quants of B.
 template <int HALF>
-__device__ __forceinline__ void dequant_q8_0(const uint8_t* p, int off, int kb, uint4* out) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(p + off + 68 * kb);  // 4-byte aligned; 17 words
+__device__ __forceinline__ void dequant_q8_0_core(const uint32_t (&w)[17], uint4* out) {
     const __half2 bias = __float2half2_rn(1152.f);
     auto cvt = [&](uint32_t q4, const __half2 d2, uint32_t& lo, uint32_t& hi) {
         const uint32_t u = q4 ^ 0x80808080u;                        // q + 128
@@ -100,30 +100,61 @@ __device__ __forceinline__ void dequant_q8_0(const uint8_t* p, int off, int kb, 
         hi = *reinterpret_cast<uint32_t*>(&hb);
     };
     if (HALF != 1) {  // block A: quants start 2 bytes into word 0
-        uint32_t r[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) r[i] = w[i];
-        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(r[0] & 0xffffu)));
+        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[0] & 0xffffu)));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const uint32_t v0 = __funnelshift_r(r[2 * c], r[2 * c + 1], 16);
-            const uint32_t v1 = __funnelshift_r(r[2 * c + 1], r[2 * c + 2], 16);
+            const uint32_t v0 = __funnelshift_r(w[2 * c], w[2 * c + 1], 16);
+            const uint32_t v1 = __funnelshift_r(w[2 * c + 1], w[2 * c + 2], 16);
             cvt(v0, d2, out[c].x, out[c].y);
             cvt(v1, d2, out[c].z, out[c].w);
         }
     }
     if (HALF != 0) {  // block B: quants are word aligned (34 + 2 = 36)
         uint4* o = out + (HALF == 2 ? 4 : 0);
-        uint32_t r[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) r[i] = w[8 + i];
-        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(r[0] >> 16)));
+        const __half2 d2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(w[8] >> 16)));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            cvt(r[1 + 2 * c], d2, o[c].x, o[c].y);
-            cvt(r[2 + 2 * c], d2, o[c].z, o[c].w);
+            cvt(w[9 + 2 * c], d2, o[c].x, o[c].y);
+            cvt(w[10 + 2 * c], d2, o[c].z, o[c].w);
         }
     }
+}
+// loader 1: 32-bit loads from the 4-byte aligned start (global memory; the skinny kernel)
+// kb: which 64-weight half of the 128-weight unit (blocks 2kb, 2kb+1)
+template <int HALF>
+__device__ __forceinline__ void dequant_q8_0(const uint8_t* p, int off, int kb, uint4* out) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p + off + 68 * kb);  // 4-byte aligned; 17 words
+    uint32_t w[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) w[i] = (HALF == 0 && i > 8) || (HALF == 1 && i < 8) ? 0u : q[i];
+    dequant_q8_0_core<HALF>(w, out);
+}
+// loader 2 (shared memory, thread = row, 144-byte rows = 9 vectors): 128-bit loads of aligned vectors, conflict free,
+// and a warp-uniform word shift (the 68-byte pair starts 0, 4, 8 or 12 bytes into a vector).  With loader 1 the 17
+// 32-bit loads of 32 rows hit 8 banks: 4-way conflicts, 61 % of the Q8_0 prefill kernel's shared-memory wavefronts.
+template <int WS>
+__device__ __forceinline__ void q8_0_gather(const uint4* v, uint32_t (&w)[17]) {
+    uint32_t a[20];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint4 t = v[i];
+        a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 17; ++i) w[i] = a[WS + i];
+}
+template <int HALF>
+__device__ __forceinline__ void dequant_q8_0_sm(const uint8_t* row16, int off, int kb, uint4* out) {
+    const int o = off + 68 * kb;   // 0, 8, 68 or 76
+    const uint4* v = reinterpret_cast<const uint4*>(row16 + (o & ~15));
+    uint32_t w[17];
+    switch ((o & 15) >> 2) {
+        case 0: q8_0_gather<0>(v, w); break;
+        case 1: q8_0_gather<1>(v, w); break;
+        case 2: q8_0_gather<2>(v, w); break;
+        default: q8_0_gather<3>(v, w); break;
+    }
+    dequant_q8_0_core<HALF>(w, out);
 }
 
 // ---- Q4_K -------------------------------------------------------------------------------------
@@ -250,7 +281,17 @@ __device__ __forceinline__ void dequant_q6_k_al(const uint8_t* b, int kb, uint4*
 // vector — conflict free with thread = row — and the words are shifted into place in registers.
 constexpr int Q6K_ROW_PITCH = 240;
 template <int WS, bool ODD>   // off = 4 WS + (ODD ? 2 : 0)
-__device__ __forceinline__ void q6k_gather(const uint4* ql, const uint4* qh, uint32_t (&lw)[16], uint32_t (&hw)[8]) {
+__device__ __forceinline__ void q6k_gather(const uint4* ql, const uint4* qh, uint32_t (&lw)[16], uint32_t (&hw)[8],
+                                           const uint4* sc, int sel, uint32_t& scw, uint32_t& dbits) {
+    {   // scales (block bytes 192..207) and d (208, 209): row bytes [192 + off, 210 + off) lie inside the two vectors sc[0..1]
+        const uint4 s0 = sc[0], s1 = sc[1];
+        const uint32_t t[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t u[5];   // the block's words 48..52 (bytes 192..211)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) u[i] = ODD ? __funnelshift_r(t[WS + i], t[WS + i + 1 < 8 ? WS + i + 1 : 7], 16) : t[WS + i];
+        scw = sel == 0 ? u[0] : sel == 1 ? u[1] : sel == 2 ? u[2] : u[3];   // sel = 2h + gp
+        dbits = u[4] & 0xffffu;
+    }
     constexpr int NL = (WS == 0 && !ODD) ? 4 : 5, NH = (WS == 0 && !ODD) ? 2 : 3;
     uint32_t a[20], c[12];
 #pragma unroll
@@ -271,23 +312,22 @@ __device__ __forceinline__ void q6k_gather(const uint4* ql, const uint4* qh, uin
 template <int HALF>
 __device__ __forceinline__ void dequant_q6_k_sm(const uint8_t* row16, int off, int kb, uint4* out) {
     const int h = kb >> 1, gp = kb & 1;
-    const uint8_t* b = row16 + off;
-    const float d = hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
-    const uint32_t scw = ld32_any(b + 192 + 8 * h + 4 * gp);
     const uint4* ql = reinterpret_cast<const uint4*>(row16 + 64 * h);
     const uint4* qh = reinterpret_cast<const uint4*>(row16 + 128 + 32 * h);
-    uint32_t lw[16], hw[8];
+    const uint4* sc = reinterpret_cast<const uint4*>(row16 + 192);
+    const int sel = 2 * h + gp;
+    uint32_t lw[16], hw[8], scw, dbits;
     switch (off >> 1) {
-        case 0: q6k_gather<0, false>(ql, qh, lw, hw); break;
-        case 1: q6k_gather<0, true>(ql, qh, lw, hw); break;
-        case 2: q6k_gather<1, false>(ql, qh, lw, hw); break;
-        case 3: q6k_gather<1, true>(ql, qh, lw, hw); break;
-        case 4: q6k_gather<2, false>(ql, qh, lw, hw); break;
-        case 5: q6k_gather<2, true>(ql, qh, lw, hw); break;
-        case 6: q6k_gather<3, false>(ql, qh, lw, hw); break;
-        default: q6k_gather<3, true>(ql, qh, lw, hw); break;
+        case 0: q6k_gather<0, false>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 1: q6k_gather<0, true>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 2: q6k_gather<1, false>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 3: q6k_gather<1, true>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 4: q6k_gather<2, false>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 5: q6k_gather<2, true>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        case 6: q6k_gather<3, false>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
+        default: q6k_gather<3, true>(ql, qh, lw, hw, sc, sel, scw, dbits); break;
     }
-    dequant_q6_k_core<HALF>(lw, hw, scw, d, gp, out);
+    dequant_q6_k_core<HALF>(lw, hw, scw, hbits2f(dbits), gp, out);
 }
 
 template <int HALF>

@@ -89,9 +89,7 @@ template <int FMT, int N, int WU, int G, int MAXT> struct Cfg {
     static constexpr int RAW = WU * U::UNIT_BYTES;       // packed bytes of one box row
     static constexpr int MAX_OFF = 16 - cgcd(RAW, 16);   // the box starts at the 16-byte aligned superset
     // + 16 for 288-byte Q4_K rows: a 304-byte pitch keeps the threads' 128-bit loads (thread = row) conflict free
-    // Q6_K: an ODD number of 16-byte vectors per row, for the same reason (the loads are 128-bit, skinny_tile.cuh)
-    static constexpr int ROW_BYTES0 = (RAW + MAX_OFF + 15) & ~15;
-    static constexpr int ROW_BYTES = ROW_BYTES0 + ((FMT == 1 && WU == 2) || (FMT == 2 && (ROW_BYTES0 / 16) % 2 == 0) ? 16 : 0);
+    static constexpr int ROW_BYTES = ((RAW + MAX_OFF + 15) & ~15) + ((FMT == 1 && WU == 2) ? 16 : 0);
     static constexpr int W_SLOT = TM * ROW_BYTES;        // bytes of a packed staging slot
     static constexpr int X_ATOM = N * 128;               // bytes of one [N tokens x 64 k] atom
     static constexpr int X_STAGE = WU * XATOMS * X_ATOM; // activations of one box column (WU steps), all N tokens
@@ -391,10 +389,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     const uint8_t* up = FMT == 1 ? brow + s * U::UNIT_BYTES : brow;
                     const int off = FMT == 1 ? 0 : static_cast<int>(((c.kb * C::RAW) & 15u) + s * U::UNIT_BYTES);
                     const uint32_t a_tmem = tmem_base + lane_base + C::A_COL0 + ab * C::A_COLS;
-                    // Q6_K: the chunk loop stays rolled — unrolled, its four bodies times the eight alignment variants of the
-                    // loader are ~150 KB of code per kernel and the three dequant groups thrash the instruction cache
-                    // (ncu: stall_no_instruction 3.4 per issue, 173 us; rolled: see profiles/)
-#pragma unroll(FMT == 2 ? 1 : C::CHUNKS)
+#pragma unroll
                     for (int kb = 0; kb < C::CHUNKS; ++kb) {
                         uint4 v[8];
                         dq64<FMT>(up, off, kb, v);

@@ -111,29 +111,6 @@ __device__ __forceinline__ void dq64_q6_k_al(const uint8_t* b, int kb, uint4 (&o
     }
     dq64_q6_k_core(lw, hw, scw, d, gp, out);
 }
-// shared memory, thread = row: conflict-free 128-bit loads of aligned vectors + register realignment (prefill_tile.cuh
-// dequant_q6_k_sm has the full story).  row16 is 16-byte aligned, the block begins `off` bytes in (even, warp-uniform).
-__device__ __forceinline__ void dq64_q6_k_sm(const uint8_t* row16, int off, int kb, uint4 (&out)[8]) {
-    const int h = kb >> 1, gp = kb & 1;
-    const uint8_t* b = row16 + off;
-    const float d = pre::hbits2f(*reinterpret_cast<const uint16_t*>(b + 208));
-    const uint32_t scw = pre::ld32_any(b + 192 + 8 * h + 4 * gp);
-    const uint4* ql = reinterpret_cast<const uint4*>(row16 + 64 * h);
-    const uint4* qh = reinterpret_cast<const uint4*>(row16 + 128 + 32 * h);
-    uint32_t lw[16], hw[8];
-    switch (off >> 1) {
-        case 0: pre::q6k_gather<0, false>(ql, qh, lw, hw); break;
-        case 1: pre::q6k_gather<0, true>(ql, qh, lw, hw); break;
-        case 2: pre::q6k_gather<1, false>(ql, qh, lw, hw); break;
-        case 3: pre::q6k_gather<1, true>(ql, qh, lw, hw); break;
-        case 4: pre::q6k_gather<2, false>(ql, qh, lw, hw); break;
-        case 5: pre::q6k_gather<2, true>(ql, qh, lw, hw); break;
-        case 6: pre::q6k_gather<3, false>(ql, qh, lw, hw); break;
-        default: pre::q6k_gather<3, true>(ql, qh, lw, hw); break;
-    }
-    dq64_q6_k_core(lw, hw, scw, d, gp, out);
-}
-
 // p: 16-byte aligned superset of the block column in this row; off: byte offset of the block inside it
 template <int FMT>
 __device__ __forceinline__ void dq64(const uint8_t* p, int off, int kb, uint4 (&out)[8]) {
@@ -145,7 +122,12 @@ __device__ __forceinline__ void dq64(const uint8_t* p, int off, int kb, uint4 (&
     } else if constexpr (FMT == 1) {
         dq64_q4_k(p, kb, out);
     } else {
-        dq64_q6_k_sm(p + (off & ~15), off & 15, kb, out);
+        // (dq64_q6_k_sm, the conflict-free loader that sped the prefill kernel up by 18 %, measured slower here: unrolled, its
+        // alignment variants thrash the instruction cache (173 us at T=16 on the lm_head), rolled it loses the overlap of
+        // one chunk's loads with the previous chunk's arithmetic (117 us); this loader: 112 us)
+        const uint8_t* b = p + off;
+        if (off & 2) dq64_q6_k_al<true>(b, kb, out);
+        else dq64_q6_k_al<false>(b, kb, out);
     }
 #endif
 }

@@ -15,9 +15,10 @@ are exchanged so that every rank ends up with the full C[T, O].  Two exchange pa
            (torch symmetric memory supplies the NVLink mappings); the receivers poll the lines themselves, so each
            transfer is one NVLink hop with no fence and no flag round trip, and kernel completion == C[T, O] complete
            on this rank.  The epoch lives in device memory, so a step is CUDA-graph capturable.
-           More tokens: NCCL broadcast of X, then the GEMM (tcgen05 skinny / prefill kernels) peer-stores each output
-           tile into the [T, O] buffers of ALL ranks (n_out outputs with ldc = O), between two symmetric-memory
-           barriers.
+           More tokens: NCCL broadcast of X, then between two symmetric-memory barriers either (slices under 1 MB) the
+           GEMM's epilogue peer-stores each output tile into the [T, O] buffers of ALL ranks (n_out outputs, ldc = O),
+           or (prefill-sized slices) the GEMM writes the rank's own buffer and the copy engines push the [T, O/N]
+           column block into every peer's buffer (ggq_push_columns: one 2-D DMA copy per peer over NVLink).
 
 `mm_fn` is injectable so the host logic (sharding arithmetic, exchange layout) is testable on CPU with
 the gloo backend and a stand-in matmul.
@@ -212,6 +213,20 @@ class NSplitLinear:
         the matching call).  Synchronises the stream."""
         return int(self._status.item()) if self.mode == "fused" else 0
 
+    DMA_MIN_BYTES = 1 << 20   # slices at least this large are exchanged by the copy engines instead of epilogue peer stores
+
+    def _push_columns(self, src: int, dsts: list[int], T: int) -> None:
+        import ctypes
+        L = self._ext.lib()
+        if not getattr(L, "_push_bound", False):
+            L.ggq_push_columns.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int64,
+                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+            L.ggq_push_columns.restype = ctypes.c_int
+            L._push_bound = True
+        arr = (ctypes.c_void_p * len(dsts))(*dsts)
+        rc = L.ggq_push_columns(src, arr, len(dsts), self.O * 2, self.per * 2, T, torch.cuda.current_stream().cuda_stream)
+        self._ext.check(rc, "ggq_push_columns")
+
     def _src_rank(self) -> int:
         """Global rank of the group's rank 0 (dist.broadcast takes global ranks)."""
         return 0 if self.group is dist.group.WORLD else dist.get_global_rank(self.group, 0)
@@ -238,8 +253,17 @@ class NSplitLinear:
             if broadcast and self.world > 1:
                 dist.broadcast(X, src=self._src_rank(), group=self.group)
             self._symm.barrier(channel=0)   # every rank has finished reading the previous result
-            self._ext.mm_ex(self._fmt_id, self.A, X, self._out_ptrs(0), self.O, self.per, T, self.K)
-            self._symm.barrier(channel=1)   # every rank's tiles have landed everywhere
+            ptrs = self._out_ptrs(0)        # own slice first, then the peers' (same columns of their buffers)
+            if T * self.per * 2 >= self.DMA_MIN_BYTES:
+                # prefill-sized slice: GEMM into the own buffer, then one 2-D DMA copy per peer (large NVLink transfers by
+                # the copy engines; peers in ring order so that no rank is everybody's first destination)
+                self._ext.mm_ex(self._fmt_id, self.A, X, ptrs[:1], self.O, self.per, T, self.K)
+                peers = ptrs[1:]
+                k = self.rank % max(1, len(peers))
+                self._push_columns(ptrs[0], peers[k:] + peers[:k], T)
+            else:
+                self._ext.mm_ex(self._fmt_id, self.A, X, ptrs, self.O, self.per, T, self.K)   # tiles peer-stored by the epilogue
+            self._symm.barrier(channel=1)   # every rank's slice has landed everywhere
             self._after_gemm = True
             return self._out[0, :T]
         if broadcast and self.world > 1:

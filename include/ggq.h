@@ -171,6 +171,16 @@ void* ggq_host_pipe_stream(ggq_host_pipe* pipe, int which);
 void ggq_host_pipe_destroy(ggq_host_pipe* pipe);
 
 /*
+ * N-split exchange of a prefill-sized result by the copy engines: the same [rows x width_bytes] column block (row pitch
+ * pitch_bytes, identical on both sides) is copied from `src` to each of the n_dst (<= 8) peer-mapped destinations with
+ * one 2-D asynchronous copy per peer on `stream`.  multigpu/nsplit.py: every rank computes its [T, O/N] slice into its
+ * own [T, O] buffer and pushes the slice into the same columns of every peer's buffer — large DMA transfers over NVLink
+ * instead of 64-byte peer stores from the GEMM epilogue (8 x B200, T=4096, O=28672: 2.0 ms -> see DESIGN.md §5).
+ */
+int ggq_push_columns(const void* src, void* const* dst, int n_dst, int64_t pitch_bytes, int64_t width_bytes, int64_t rows,
+                     void* stream);
+
+/*
  * Dequantize packed rows to fp16 [O, K] with the SAME device functions the prefill GEMM uses.
  * Bit-exact targets: utils/quantize/q8_0.py:52-100 dequantize_q8_0, q4_k.py:146-158 dequantize_q4_k,
  * q6_k.py:138-159 dequantize_q6_k (fp32 there; `.half()` of it here).

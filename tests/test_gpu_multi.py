@@ -58,7 +58,8 @@ def _worker(rank, world, port, fmt, O, T, K, mode, q):
 
 
 @pytest.mark.parametrize("mode", ["nccl", "fused"])
-@pytest.mark.parametrize("fmt,O,T,K", [("q4_k", 4096, 1, 4096), ("q6_k", 2048, 8, 2048), ("q8_0", 1024, 256, 1024)])
+@pytest.mark.parametrize("fmt,O,T,K", [("q4_k", 4096, 1, 4096), ("q6_k", 2048, 8, 2048), ("q8_0", 1024, 256, 1024),
+                                        ("q4_k", 8192, 512, 2048)])   # the last: slices >= 1 MB, pushed by the copy engines
 def test_nsplit_two_gpus(mode, fmt, O, T, K):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
