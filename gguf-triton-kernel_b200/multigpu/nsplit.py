@@ -216,6 +216,8 @@ class NSplitLinear:
     DMA_MIN_BYTES = 1 << 20   # slices at least this large are exchanged by the copy engines instead of epilogue peer stores
 
     def _push_columns(self, src: int, dsts: list[int], T: int) -> None:
+        """One 2-D DMA copy per peer, each on its own side stream (several copy engines at once); the current stream
+        continues when all of them are done."""
         import ctypes
         L = self._ext.lib()
         if not getattr(L, "_push_bound", False):
@@ -223,9 +225,19 @@ class NSplitLinear:
                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
             L.ggq_push_columns.restype = ctypes.c_int
             L._push_bound = True
-        arr = (ctypes.c_void_p * len(dsts))(*dsts)
-        rc = L.ggq_push_columns(src, arr, len(dsts), self.O * 2, self.per * 2, T, torch.cuda.current_stream().cuda_stream)
-        self._ext.check(rc, "ggq_push_columns")
+        if getattr(self, "_push_streams", None) is None:
+            self._push_streams = [torch.cuda.Stream(device=self.A.device) for _ in dsts]
+            self._push_done = [torch.cuda.Event() for _ in dsts]
+            self._gemm_done = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._gemm_done.record(main)
+        for st, ev, dst in zip(self._push_streams, self._push_done, dsts):
+            st.wait_event(self._gemm_done)
+            one = (ctypes.c_void_p * 1)(dst)
+            rc = L.ggq_push_columns(src, one, 1, self.O * 2, self.per * 2, T, st.cuda_stream)
+            self._ext.check(rc, "ggq_push_columns")
+            ev.record(st)
+            main.wait_event(ev)
 
     def _src_rank(self) -> int:
         """Global rank of the group's rank 0 (dist.broadcast takes global ranks)."""
