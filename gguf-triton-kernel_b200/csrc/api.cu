@@ -124,6 +124,7 @@ static MmArgs placeholder_args(int64_t O, int64_t T, int64_t K) {
 
 static int dequant(int fmt, const void* W, void* out, int64_t O, int64_t K, void* stream) {
     if (O < 0 || K < 0 || K % fmt_qk(fmt) != 0) return GGQ_E_SHAPE;
+    if (K > (int64_t{1} << 30)) return GGQ_E_SHAPE;   // the kernels index a row with 32-bit arithmetic
     if (O == 0 || K == 0) return 0;
     if (!W || !out) return GGQ_E_POINTER;
     return launch_dequant(fmt, static_cast<const uint8_t*>(W), out, O, K, static_cast<cudaStream_t>(stream));

@@ -782,6 +782,15 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
         const int S = c2 ? atoi(c2 + 1) : 1;
         return make_plan_cfg<FMT>(a, T, nw, occ, nw == 8 && occ == 1 && S == 1, pl, S);
     }
+    // small problems (a handful of (tile, chunk) items per warp): the weights are on chip before the activations are and
+    // the launch is bound by how many warps unpack them — 16 resident warps (two 8-warp CTAs) beat 12 (measured,
+    // Q4_K 14336 x 4096 T=1: 11.4 vs 12.2 us; 4096 x 4096: 6.0 vs 6.4 us); large ones stream best with 12 warps x 3 stages
+    {
+        using G = Geo<FMT>;
+        const int64_t nc = (a.K / G::QK + G::CHUNK_BLOCKS - 1) / G::CHUNK_BLOCKS;
+        const int64_t items_per_warp = ((a.O + 15) / 16) * nc / (static_cast<int64_t>(num_sms()) * 12);
+        if (items_per_warp < 8 && !a.sync && make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
+    }
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 3) return true;
     if (make_plan_cfg<FMT>(a, T, 8, 2, false, pl)) return true;
     if (make_plan_cfg<FMT>(a, T, 12, 1, false, pl) && pl.p.stages >= 2) return true;

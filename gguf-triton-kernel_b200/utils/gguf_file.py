@@ -30,7 +30,9 @@ DEFAULT_ALIGNMENT = 32
 _SCALARS = {0: "<B", 1: "<b", 2: "<H", 3: "<h", 4: "<I", 5: "<i", 6: "<f", 7: "<?", 10: "<Q", 11: "<q", 12: "<d"}
 _T_STRING, _T_ARRAY = 8, 9
 
-# ggml tensor types: id -> (name, elements per block, bytes per block); Q8_1 as a file type carries fp32 d and s
+# ggml tensor types: id -> (name, elements per block, bytes per block).  Q8_1: gguf-py's table (the file-format authority
+# this reader is tested against) says 40 B (fp32 d and s); ggml's in-memory block_q8_1 — what ggq_quantize_q8_1_f16 and the
+# reference's q8_1.py produce — is 36 B (fp16 d, s).  Q8_1 is an activation format and does not occur in weight files.
 GGML_TYPES = {
     0: ("F32", 1, 4), 1: ("F16", 1, 2), 2: ("Q4_0", 32, 18), 3: ("Q4_1", 32, 20), 6: ("Q5_0", 32, 22),
     7: ("Q5_1", 32, 24), 8: ("Q8_0", 32, 34), 9: ("Q8_1", 32, 40), 10: ("Q2_K", 256, 84), 11: ("Q3_K", 256, 110),

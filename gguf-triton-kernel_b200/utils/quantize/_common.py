@@ -62,5 +62,9 @@ def dequant(fmt: str, q: torch.Tensor, shape, blk: int, qk: int) -> torch.Tensor
     n = q.numel()
     if n % blk != 0:
         raise ValueError(f"Invalid quantized tensor size. Expected size divisible by {blk}, got {n}.")
-    elems = n // blk * qk
-    return _ext.dequant(_ext.FMT_ID[fmt], q.contiguous(), 1, elems).reshape(shape)
+    nb = n // blk
+    # rows of at most 2^20 blocks: the C ABI carries K as a 32-bit quantity inside its kernels (GGQ_E_SHAPE beyond)
+    per = nb
+    while per > (1 << 20) and per % 2 == 0:
+        per //= 2
+    return _ext.dequant(_ext.FMT_ID[fmt], q.contiguous(), nb // per, per * qk).reshape(shape)

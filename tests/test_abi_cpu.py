@@ -159,3 +159,12 @@ def test_torch_extension_loads_and_checks_operands():
         mmq_q4_k_swiglu(A, A, B, 1, 1, 256)
     with pytest.raises(AssertionError):
         mmq_q4_k_swiglu(A, A, B, 1, 1, 100)
+
+
+def test_dequant_rejects_rows_beyond_32_bit_indexing():
+    """K beyond what the kernels index with 32-bit arithmetic is an error, not a silent overflow."""
+    from kernels import _ext
+    L = _ext.lib()
+    one = ctypes.c_void_p(256)
+    assert L.ggq_dequant_q4_k_f16(one, one, 1, (1 << 31), None) == -1
+    assert L.ggq_dequant_q8_0_f16(one, one, 1, (1 << 30) + 32, None) == -1

@@ -9,7 +9,7 @@ from dev_skinny import gen_weights, timed, BLK
 fmt, O, K, T = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 fam = int(sys.argv[5]) if len(sys.argv) > 5 else ext.FAMILY_SKINNY
 nbytes = O * (K // BLK[fmt][0]) * BLK[fmt][1]
-copies = max(1, min(8, -(-2 * 126_000_000 // nbytes)))
+copies = max(1, min(16, -(-2 * 126_000_000 // nbytes)))
 Ws = [gen_weights(fmt, O, K, 7 + i) for i in range(copies)]
 X = torch.randn((T, K), device="cuda", dtype=torch.float16)
 C = torch.empty((T, O), device="cuda", dtype=torch.float16)
