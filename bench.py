@@ -355,6 +355,40 @@ def swiglu_cell(torch, ext, name, fmt, o, k, ts, hbm_peak, seed=17):
     return cells
 
 
+def q8_1_cell(torch, ext, name, fmt, o, k, t, hbm_peak, W):
+    """The reference-arithmetic mode (Q8_1 activations, integer block dots, fp16 accumulator: ggq_mm_ref_q8_1), timed on
+    the device; parity = BIT-IDENTICAL to the oracle's port of kernels/cpu_impls on sampled rows."""
+    from kernels import q8_1_mode
+    from oracle import ggq_oracle as orc
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    fn = {"q8_0": q8_1_mode.mmq_q8_0_q8_1, "q4_k": q8_1_mode.mmq_q4_k_q8_1, "q6_k": q8_1_mode.mmq_q6_k_q8_1}[fmt]
+    X = torch.randn((t, k), device="cuda", dtype=torch.float16)
+    XQ = quantize_to_q8_1(X)
+    W2 = W.clone()
+    C = fn(W, XQ, o, t, k)
+    torch.cuda.synchronize()
+    pick = sample_rows(o, 48)
+    rb = packed_bytes(fmt, 1, k)
+    Wc = W.view(-1, rb)[torch.from_numpy(pick).to(W.device)].cpu().numpy().reshape(-1)
+    want = np.ascontiguousarray(orc.mmq_cpu(fmt, Wc, X.cpu().numpy(), len(pick), t, k))
+    got = np.ascontiguousarray(C[:, torch.from_numpy(pick).to(C.device)].cpu().numpy())
+    same = bool(np.array_equal(got.view(np.uint16), want.view(np.uint16)))
+    it = [0]
+
+    def step():
+        it[0] += 1
+        fn(W if it[0] & 1 else W2, XQ, o, t, k)
+    ms = timed(torch, None, step, 10, 3, 1)
+    nbytes = packed_bytes(fmt, o, k)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    del W2
+    torch.cuda.empty_cache()
+    return {"cell": f"q8_1-mode {name} T={t}", "family": "reference arithmetic (Q8_1 activations, DP4A block dots, fp16 accumulator)",
+            "fmt": fmt, "O": o, "K": k, "T": t, "us": round(ms * 1e3, 2), "achieved": round(gbs, 1), "unit": "GB/s",
+            "peak": hbm_peak, "frac": round(gbs / hbm_peak, 3), "frac_8TBps": round(gbs / 8000.0, 3),
+            "parity": {"bit_identical_to_cpu_impls_port": same, "rows_sampled": int(len(pick)), "ok": same}}
+
+
 def single_gpu_cells(torch, ext, hbm_peak, tf_peak, W_head):
     cells = []
     # BASELINE configs[1] / [2] / [3]: decode, three quant types, M = 1..16
@@ -370,6 +404,9 @@ def single_gpu_cells(torch, ext, hbm_peak, tf_peak, W_head):
     cells.append(prefill_cell(torch, ext, "Q8_0 FFN 28672x8192", "q8_0", 28672, 8192, 4096, tf_peak))
     cells.append(prefill_cell(torch, ext, "Q6_K down_proj 4096x14336", "q6_k", 4096, 14336, 2048, tf_peak))
     cells.append(prefill_cell(torch, ext, "Q6_K lm_head 128256x4096", "q6_k", 128256, 4096, 2048, tf_peak))
+    # the reference's own arithmetic (Q8_1 activations) on the headline layer
+    cells.append(q8_1_cell(torch, ext, "Q4_K lm_head 128256x4096", "q4_k", 128256, 4096, 1, hbm_peak, W_head))
+    cells.append(q8_1_cell(torch, ext, "Q4_K lm_head 128256x4096", "q4_k", 128256, 4096, 8, hbm_peak, W_head))
     # the fused SwiGLU up-projection on the Llama-3-8B / 70B FFN shapes
     cells += swiglu_cell(torch, ext, "Q4_K FFN gate+up 2x14336x4096", "q4_k", 14336, 4096, (1, 8), hbm_peak)
     cells += swiglu_cell(torch, ext, "Q4_K FFN gate+up 2x28672x8192", "q4_k", 28672, 8192, (1, 8), hbm_peak)

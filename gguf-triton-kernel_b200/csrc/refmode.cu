@@ -1,11 +1,17 @@
 // refmode.cu — "reference arithmetic" mode: Q8_1-quantized activations, integer block dots, fp16 accumulation,
 // in exactly the operation order of the reference's CPU implementations, so the result equals
-// kernels/cpu_impls/mmq_*_q8_1_cpu bit for bit.  One thread per output element walks the
-// blocks sequentially; this is a parity tool, not a fast path.
+// kernels/cpu_impls/mmq_*_q8_1_cpu bit for bit.  One thread per output element walks the blocks
+// sequentially — the fp16 accumulation chain of an output IS sequential in the reference — and consecutive threads own
+// consecutive weight rows of the same token.  Two kernels: `refmode_fast_kernel` (rows that are whole 32-bit words:
+// 128-bit / 32-bit vector loads, the integer block dots on DP4A, the activation block read once per warp as a broadcast)
+// and the byte-wise `refmode_kernel` for every other shape.  The integer dots are exact in any order; the floating-point
+// operations are the same explicitly rounded intrinsics in the same order in both.
 //   Q8_0  kernels/cpu_impls/mmq_q8_0_q8_1_cpu.py:37-54   r = fp16(fp16(d_w*d_x) * dot);            C = fp16(C + r)
 //   Q4_K  kernels/cpu_impls/mmq_q4_k_q8_1_cpu.py:94-117  r = ((d*sc)*d_x)*dot - (dmin*m)*s_x (fp32); C = fp16(C + fp16(r))
 //   Q6_K  kernels/cpu_impls/mmq_q6_k_q8_1_cpu.py:117-150 r = d_x*((d*sc1)*dot1 + (d*sc2)*dot2) (fp32); C = fp16(C + fp16(r))
 // Every fp32 operation is an explicitly rounded intrinsic (__fmul_rn / __fadd_rn / __fsub_rn): no FMA contraction.
+#include <cstdlib>
+
 #include "../../include/ggq.h"
 #include "common.cuh"
 #include "formats.cuh"
@@ -79,6 +85,169 @@ __global__ void __launch_bounds__(128) refmode_kernel(const uint8_t* __restrict_
     C[t * O + o] = __float2half_rn(c);
 }
 
+// ---- vectorised form -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float hlo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu))); }
+__device__ __forceinline__ float hhi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
+__device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return __dp4a(static_cast<int>(a), static_cast<int>(b), c); }
+// n + 1 words from the 4-byte aligned address at or 2 bytes below p, shifted so that out[i] = the word at p + 4 i
+template <int N>
+__device__ __forceinline__ void ld_words(const uint8_t* p, uint32_t (&out)[N]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t{3});
+    if ((a & 2) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = __ldg(q + i);
+    } else {
+        uint32_t prev = __ldg(q);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t next = __ldg(q + i + 1);
+            out[i] = __funnelshift_r(prev, next, 16);
+            prev = next;
+        }
+    }
+}
+
+// Requirements (checked by the launcher): W 16-byte aligned, XQ 4-byte aligned, rows whole 32-bit words (Q8_0 / Q6_K: an
+// even number of blocks per row).  A thread owns ONE weight row and TT consecutive tokens: the row's blocks are loaded and
+// unpacked once per block, the activation words are warp-uniform loads (every lane of a warp reads the same address).
+template <int FMT, int TT>
+__global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __restrict__ W, const uint8_t* __restrict__ XQ,
+                                                           __half* __restrict__ C, int64_t O, int64_t T, int64_t K) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t groups = (T + TT - 1) / TT;
+    if (idx >= O * groups) return;
+    const int64_t o = idx % O, t0 = (idx / O) * TT;
+    const int nt = static_cast<int>(T - t0 < TT ? T - t0 : TT);   // warp-uniform unless the warp straddles two token groups
+    const int64_t nb32 = K / 32;
+    const int64_t xstride = nb32 * 9;                                               // words per token
+    const uint32_t* xrow = reinterpret_cast<const uint32_t*>(XQ) + t0 * xstride;    // 9 words per Q8_1 block: {d, s}, qs[32]
+    float c[TT];
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) c[tt] = 0.f;
+    if (FMT == GGQ_Q8_0) {
+        const uint32_t* wrow = reinterpret_cast<const uint32_t*>(W + o * nb32 * 34);
+        for (int64_t b = 0; b < nb32; b += 2) {   // two blocks = 68 bytes = 17 words
+            uint32_t w[17], q[2][8];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) w[i] = __ldg(wrow + (b >> 1) * 17 + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                q[0][i] = __funnelshift_r(w[i], w[i + 1], 16);
+                q[1][i] = w[9 + i];
+            }
+            const float dw[2] = {hlo(w[0]), hhi(w[8])};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt) {
+                    if (tt >= nt) break;
+                    const uint32_t* xb = xrow + tt * xstride + (b + half) * 9;
+                    const uint32_t x0 = __ldg(xb);
+                    int dot = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dot = dp4(q[half][i], __ldg(xb + 1 + i), dot);
+                    const float sc = __half2float(__float2half_rn(__fmul_rn(dw[half], hlo(x0))));  // fp16 * fp16 -> fp16
+                    c[tt] = acc16(c[tt], __fmul_rn(sc, static_cast<float>(dot)));
+                }
+            }
+        }
+    } else if (FMT == GGQ_Q4_K) {
+        const uint4* wrow = reinterpret_cast<const uint4*>(W + o * (K / 256) * 144);   // 9 vectors per super-block
+        for (int64_t sb = 0; sb < K / 256; ++sb) {
+            const uint4 h = __ldg(wrow + sb * 9);
+            const float d = hlo(h.x), dmin = hhi(h.x);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {   // sub-blocks 2 pr (low nibbles) and 2 pr + 1 (high nibbles) share 32 bytes
+                const uint4 qa = __ldg(wrow + sb * 9 + 1 + 2 * pr), qb = __ldg(wrow + sb * 9 + 2 + 2 * pr);
+                const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int j = 2 * pr + hf;
+                    int sc, m;   // q4_k_ref.c:174-186, from the header words h.y = s[0..3], h.z = s[4..7], h.w = s[8..11]
+                    if (j < 4) {
+                        sc = (h.y >> (8 * j)) & 63;
+                        m = (h.z >> (8 * j)) & 63;
+                    } else {
+                        const int sh = 8 * (j - 4);
+                        sc = ((h.w >> sh) & 0x0F) | ((((h.y >> sh) & 0xFF) >> 6) << 4);
+                        m = (((h.w >> sh) & 0xFF) >> 4) | ((((h.z >> sh) & 0xFF) >> 6) << 4);
+                    }
+                    uint32_t q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = (hf ? (w[i] >> 4) : w[i]) & 0x0F0F0F0Fu;
+                    const float dsc = __fmul_rn(d, static_cast<float>(sc)), dm = __fmul_rn(dmin, static_cast<float>(m));
+#pragma unroll
+                    for (int tt = 0; tt < TT; ++tt) {
+                        if (tt >= nt) break;
+                        const uint32_t* xb = xrow + tt * xstride + (sb * 8 + j) * 9;
+                        const uint32_t x0 = __ldg(xb);
+                        int dot = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dot = dp4(q[i], __ldg(xb + 1 + i), dot);
+                        const float t1 = __fmul_rn(__fmul_rn(dsc, hlo(x0)), static_cast<float>(dot));
+                        const float t2 = __fmul_rn(dm, hhi(x0));
+                        c[tt] = acc16(c[tt], __fsub_rn(t1, t2));
+                    }
+                }
+            }
+        }
+    } else {
+        const uint8_t* wrow = W + o * (K / 256) * 210;
+        for (int64_t sb = 0; sb < K / 256; ++sb) {
+            const uint8_t* wb = wrow + sb * 210;   // 2-byte aligned (odd blocks of a row start 2 bytes into a word)
+            uint32_t scw[5];                       // bytes 192..211: 16 int8 scales, d
+            ld_words<5>(wb + 192, scw);
+            const float d = hlo(scw[4]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t ql[16], qh[8];
+                ld_words<16>(wb + 64 * h, ql);
+                ld_words<8>(wb + 128 + 32 * h, qh);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {      // j = 4 h + g: weights 128 h + 32 g + l, l = 0..31 (q6_k_ref.c:320-336)
+                    const int j = 4 * h + g;
+                    uint32_t q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t lo = (ql[8 * (g & 1) + i] >> (4 * (g >> 1))) & 0x0F0F0F0Fu;
+                        const uint32_t hi = ((qh[i] >> (2 * g)) & 0x03030303u) << 4;
+                        q[i] = __vsub4(lo | hi, 0x20202020u);   // q6 - 32 in every byte, as int8
+                    }
+                    const uint32_t s2 = (scw[j >> 1] >> (16 * (j & 1))) & 0xffffu;   // scales 2 j, 2 j + 1
+                    const float s1 = __fmul_rn(d, static_cast<float>(static_cast<int>(static_cast<int8_t>(s2 & 0xffu))));
+                    const float s2f = __fmul_rn(d, static_cast<float>(static_cast<int>(static_cast<int8_t>(s2 >> 8))));
+#pragma unroll
+                    for (int tt = 0; tt < TT; ++tt) {
+                        if (tt >= nt) break;
+                        const uint32_t* xb = xrow + tt * xstride + (sb * 8 + j) * 9;
+                        const uint32_t x0 = __ldg(xb);
+                        int dot1 = 0, dot2 = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            dot1 = dp4(q[i], __ldg(xb + 1 + i), dot1);
+                            dot2 = dp4(q[4 + i], __ldg(xb + 5 + i), dot2);
+                        }
+                        const float inner = __fadd_rn(__fmul_rn(s1, static_cast<float>(dot1)), __fmul_rn(s2f, static_cast<float>(dot2)));
+                        c[tt] = acc16(c[tt], __fmul_rn(hlo(x0), inner));
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt)
+        if (tt < nt) C[(t0 + tt) * O + o] = __float2half_rn(c[tt]);
+}
+
+template <int FMT>
+static void launch_fast(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
+    auto grid = [&](int tt) { return static_cast<unsigned>((O * ((T + tt - 1) / tt) + 127) / 128); };
+    if (T == 1) refmode_fast_kernel<FMT, 1><<<grid(1), 128, 0, s>>>(w, x, c, O, T, K);
+    else if (T <= 4) refmode_fast_kernel<FMT, 4><<<grid(4), 128, 0, s>>>(w, x, c, O, T, K);
+    else refmode_fast_kernel<FMT, 8><<<grid(8), 128, 0, s>>>(w, x, c, O, T, K);
+}
+
 }  // namespace ggq
 
 using namespace ggq;
@@ -90,11 +259,25 @@ extern "C" int ggq_mm_ref_q8_1(int fmt, const void* W, const void* XQ, void* C, 
     if (O == 0 || T == 0) return 0;
     if (!W || !XQ || !C) return GGQ_E_POINTER;
     const int64_t n = O * T;
+    if ((n + 127) / 128 > 0x7fffffff) return GGQ_E_SHAPE;
     const unsigned grid = static_cast<unsigned>((n + 127) / 128);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint8_t* w = static_cast<const uint8_t*>(W);
     const uint8_t* x = static_cast<const uint8_t*>(XQ);
     __half* c = static_cast<__half*>(C);
+    static const bool slow = getenv("GGQ_REFMODE_BYTEWISE") != nullptr;   // dev: always the byte-wise kernel
+    const int64_t nb = K / fmt_qk(fmt);
+    const bool vec_ok = !slow && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(XQ) & 3) == 0 &&
+                        (fmt == GGQ_Q4_K || nb % 2 == 0);
+    if (vec_ok) {
+        switch (fmt) {
+            case GGQ_Q8_0: launch_fast<GGQ_Q8_0>(w, x, c, O, T, K, s); break;
+            case GGQ_Q4_K: launch_fast<GGQ_Q4_K>(w, x, c, O, T, K, s); break;
+            default: launch_fast<GGQ_Q6_K>(w, x, c, O, T, K, s); break;
+        }
+        count_launch();
+        return static_cast<int>(cudaGetLastError());
+    }
     switch (fmt) {
         case GGQ_Q8_0: refmode_kernel<GGQ_Q8_0><<<grid, 128, 0, s>>>(w, x, c, O, T, K); break;
         case GGQ_Q4_K: refmode_kernel<GGQ_Q4_K><<<grid, 128, 0, s>>>(w, x, c, O, T, K); break;

@@ -80,6 +80,23 @@ def test_reference_arithmetic_mode_is_bit_identical(golden, fmt):
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
 
 
+@pytest.mark.parametrize("fmt", ("q8_0", "q4_k", "q6_k"))
+@pytest.mark.parametrize("M,N,K", [(300, 3, 4096), (33, 1, 512), (70, 2, 768), (16, 17, 1280)])
+def test_reference_arithmetic_mode_both_kernels(fmt, M, N, K):
+    """The vectorised kernel (rows that are whole words: K/QK even, always for Q4_K) and the byte-wise one (K = 768, 1280:
+    odd block counts for Q6_K / Q4_K-sized super-blocks) are both bit-identical to the oracle's kernels/cpu_impls port;
+    M not a multiple of 32 mixes tokens inside a warp."""
+    from kernels import q8_1_mode
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    fn = {"q8_0": q8_1_mode.mmq_q8_0_q8_1, "q4_k": q8_1_mode.mmq_q4_k_q8_1, "q6_k": q8_1_mode.mmq_q6_k_q8_1}[fmt]
+    A = orc.random_blocks(fmt, M, K, seed=M + N)
+    X = np.random.default_rng(K).standard_normal((N, K)).astype(np.float16)
+    Bq = quantize_to_q8_1(torch.from_numpy(X).cuda())
+    got = fn(torch.from_numpy(A).cuda(), Bq, M, N, K).cpu().numpy()
+    want = np.ascontiguousarray(orc.mmq_cpu(fmt, A, X, M, N, K))
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (fmt, M, N, K)
+
+
 def _kq_cases():
     rng = np.random.default_rng(1)
     n = 256 * 512
