@@ -72,8 +72,13 @@ template <int FMT> struct Geo;
 template <> struct Geo<0> {  // Q8_0: 16 blocks = 512 weights = 544 B in one TMA box of 560 B (16 B of the next chunk ride along so
                              // that slot/4 % 32 == 12 and the lanes' 32-bit loads are conflict free; measured faster than
                              // two 272 B boxes: TMA cost is per box row)
-    static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = 16, CHUNK_ELEMS = 512, CHUNK_BYTES = 544, SLOT = 560;
-    static constexpr int PREP_BLOCKS = 16;      // blocks handled per prep/compute sub-step (= one TMA box) of a stage
+#ifndef GGQ_Q8_0_CHUNK
+#define GGQ_Q8_0_CHUNK 16
+#endif
+    // (GGQ_Q8_0_CHUNK = 8: 272 B chunks in 304 B slots, the same bank pattern — slot/4 % 32 == 12)
+    static constexpr int QK = 32, BLK = 34, CHUNK_BLOCKS = GGQ_Q8_0_CHUNK, CHUNK_ELEMS = 32 * CHUNK_BLOCKS,
+                         CHUNK_BYTES = 34 * CHUNK_BLOCKS, SLOT = CHUNK_BLOCKS == 16 ? 560 : 304;
+    static constexpr int PREP_BLOCKS = CHUNK_BLOCKS;      // blocks handled per prep/compute sub-step (= one TMA box) of a stage
     static constexpr int GROUP = 32;            // activations per pre-summed group (one block)
     static constexpr int SCRATCH_PER_BLOCK = 0;  // bytes of prepared scales per (row, block)
     static constexpr float TBL_MUL = -128.f / 16777216.f;   // cancels the +128 of (q ^ 0x80)

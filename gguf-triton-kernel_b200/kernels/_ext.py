@@ -13,7 +13,7 @@ import os
 
 import torch
 
-_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PKG = os.environ.get("GGQ_LIB_DIR") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # (dev: A/B builds)
 _LIB_PATH = os.path.join(_PKG, "libggq.so")
 _lib = None
 _text = None
