@@ -331,12 +331,13 @@ int ggq_describe(int fmt, int64_t O, int64_t T, int64_t K, char* out, int cap) {
             return 0;
         case GGQ_FAMILY_DECODE: {
             int v[9];
-            if (decode_plan(fmt, a, v) != 0) return GGQ_E_FAMILY;
+            bool wide = false;
+            if (decode_plan(fmt, a, v, &wide) != 0) return GGQ_E_FAMILY;
             const int tt = static_cast<int>(T > 16 ? 16 : T);
             const bool gv = tt == 1 && v[1] == 1 && v[3] == 1;
-            snprintf(out, cap, "ggq::dec::decode_kernel<%s,NT=%d,AT=%d,%s> grid=%d occ=%d stages=%d k-slices=%d%s", names[fmt], v[2],
-                     v[1], gv ? "GV=1 (single-token GEMV tile code)" : "GV=0", v[6] / 100, v[6] % 100, v[5], v[3],
-                     T > 16 ? " (16-token passes)" : "");
+            snprintf(out, cap, "ggq::dec::decode_kernel<%s,NT=%d,AT=%d,%s%s> grid=%d occ=%d stages=%d k-slices=%d%s", names[fmt], v[2],
+                     v[1], gv ? "GV=1 (single-token GEMV tile code)" : "GV=0", wide ? ",WIDE (4-block stages)" : "", v[6] / 100,
+                     v[6] % 100, v[5], v[3], T > 16 ? " (16-token passes)" : "");
             return 0;
         }
     }

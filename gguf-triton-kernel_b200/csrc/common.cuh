@@ -62,7 +62,7 @@ int launch_skinny(int fmt, const MmArgs& a);
 bool decode_supports(int fmt, const MmArgs& a);
 bool prefill_supports(int fmt, const MmArgs& a);
 bool skinny_supports(int fmt, const MmArgs& a);
-int decode_plan(int fmt, const MmArgs& a, int* out9);
+int decode_plan(int fmt, const MmArgs& a, int* out9, bool* wide = nullptr);   // wide: the Q4_K wide-chunk GEMV geometry
 void decode_set_trace(void* buf);
 int skinny_describe(int fmt, const MmArgs& a, char* out, int cap);
 

@@ -18,13 +18,18 @@ bool decode_supports(int fmt, const MmArgs& a) {
 
 // Host-only view of the decode planner (tests / DESIGN.md): out = {KW, AT, NT, slices, chunks per
 // slice, stages, grid, batches, smem bytes}.  Returns 0, or GGQ_E_FAMILY when no plan fits.
-int decode_plan(int fmt, const MmArgs& a, int* out) {
+int decode_plan(int fmt, const MmArgs& a, int* out, bool* wide) {
     dec::Plan pl;
+    if (wide) *wide = false;
     const int T = static_cast<int>(a.T > 16 ? 16 : a.T);
     bool ok = false;
     switch (fmt) {
         case GGQ_Q8_0: ok = dec::make_plan<0>(a, T, pl); break;
-        case GGQ_Q4_K: ok = dec::make_plan<1>(a, T, pl); break;
+        case GGQ_Q4_K:
+            ok = dec::make_plan_wide(a, T, pl);
+            if (ok && wide) *wide = true;
+            if (!ok) ok = dec::make_plan<1>(a, T, pl);
+            break;
         case GGQ_Q6_K: ok = dec::make_plan<2>(a, T, pl); break;
     }
     if (!ok) return GGQ_E_FAMILY;

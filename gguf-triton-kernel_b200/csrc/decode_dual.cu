@@ -32,6 +32,12 @@ template <int FMT>
 static int launch_fmt_dual(const MmArgs& a, bool plan_only) {
     Plan pl;
     const int T = static_cast<int>(a.T);
+    if constexpr (FMT == 1) {
+        if (make_plan_wide(a, T, pl)) {   // Q4_K single token on large layers: the wide-chunk geometry (decode_impl.cuh)
+            if (plan_only) return 0;
+            return launch_kernel<1, 1, 1, 8, 1, true, true, true>(pl, a.stream, a.W2);
+        }
+    }
     if (!make_plan_dual<FMT>(a, T, pl) || pl.at != 1) return GGQ_E_FAMILY;
     if (plan_only) return 0;
     if (T == 1 && pl.p.n_slices == 1)

@@ -46,6 +46,16 @@ constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
 constexpr int SMEM_LIMIT_2 = 113 * 1024;  // per CTA when two CTAs share an SM (228 KB - 2 x 1 KB reserved)
 
+// Kernel geometry = the format's tile geometry (decode_tile.cuh) with the CHUNK — what one ring stage holds of a row —
+// optionally doubled.  WIDE (Q4_K single-token GEMV on large layers): 4 blocks = 576 B per row and stage, filled by two
+// back-to-back 288 B boxes: DRAM sees 576 contiguous bytes per row and request, and the per-chunk control code runs half
+// as often (measured: lm_head 51.8 -> 49.4 us, 28672 x 8192 27.9 -> 26.5 us; with T = 8 the same geometry loses 30 %,
+// gpurun_out/r2_ab.log).  The lane-level tile code only knows PREP_BLOCKS / SLOT and is the same for both.
+template <int FMT, bool WIDE> struct KGeo : Geo<FMT> {};
+template <> struct KGeo<1, true> : Geo<1> {
+    static constexpr int CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576;
+};
+
 struct Params {
     const uint8_t* W;
     const uint8_t* X;
@@ -110,13 +120,13 @@ __device__ __forceinline__ uint2 ll_wait(const uint4* src, uint32_t flag, const 
 // DUAL: fused SwiGLU up-projection (ggq_mm_swiglu).  A tile is 8 rows of the gate matrix (map_w, MMA rows 0..7) over
 // the SAME 8 rows of the up matrix (map_w2, MMA rows 8..15): the m16n8 accumulator fragment of a lane then holds
 // gate[row g] in v[0..1] and up[row g] in v[2..3], and the store writes silu(gate) * up — no extra pass, no extra traffic.
-template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false, bool DUAL = false>
+template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false, bool DUAL = false, bool WIDE = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w2, const Params p) {
     static_assert(!GV || (NT == 1 && AT == 1), "the GEMV tile code is single-token, one live tile");
     static_assert(!DUAL || AT == 1, "the fused SwiGLU store is part of the flat (tile, chunk) walk");
     constexpr int TILE_ROWS = DUAL ? 8 : 16;   // output rows per tile
-    using G = Geo<FMT>;
+    using G = KGeo<FMT, WIDE>;
     constexpr int SUBTILES = G::CHUNK_BLOCKS / G::PREP_BLOCKS;  // TMA boxes per stage
     constexpr int STAGE_BYTES = SUBTILES * 16 * G::SLOT;
     constexpr int SCR_BYTES = 16 * G::PREP_BLOCKS * G::SCRATCH_PER_BLOCK;
@@ -333,6 +343,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
 #pragma unroll
             for (int u = 0; u < SUBTILES; ++u) {
                 s.rows = ring + cstage * STAGE_BYTES + u * 16 * G::SLOT;
+                s.data_off = ((b0 + u * G::PREP_BLOCKS) * G::BLK) & 15;
                 s.nblk = G::PREP_BLOCKS;
                 s.k0 = ci * G::CHUNK_ELEMS + u * G::PREP_BLOCKS * G::QK;
                 Tile<FMT, NT, GV>::template prep<true>(L, s);
@@ -347,6 +358,7 @@ decode_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__
                 const int b = u * G::PREP_BLOCKS;
                 if (b < nblk) {
                     s.rows = ring + cstage * STAGE_BYTES + u * 16 * G::SLOT;
+                    s.data_off = ((b0 + b) * G::BLK) & 15;
                     s.nblk = min(G::PREP_BLOCKS, nblk - b);
                     s.k0 = ci * G::CHUNK_ELEMS + b * G::QK;
                     Tile<FMT, NT, GV>::template prep<false>(L, s);
@@ -663,9 +675,9 @@ struct Plan {
 };
 
 // One configuration attempt: NW warps per CTA, OCC CTAs per SM.
-template <int FMT>
+template <int FMT, bool WIDE = false>
 static bool make_plan_cfg(const MmArgs& a, int T, int NW, int OCC, bool allow_slicing, Plan& pl, int S = 1) {
-    using G = Geo<FMT>;
+    using G = KGeo<FMT, WIDE>;
     Params& p = pl.p;
     p = Params{};
     p.W = a.W;
@@ -817,9 +829,21 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
 }
 
-template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false, bool DUAL = false>
+// Q4_K single-token GEMV on large layers: the wide-chunk geometry (KGeo<1, true>), 8 warps x 2 stages of 9.2 KB (10 warps
+// measured slower: 53.5 vs 49.5 us on the lm_head).  Small layers (fewer than 8 wide items per warp) keep the
+// fine-grained geometry; shapes whose activations do not fit next to the wide rings fall back as well.
+static bool make_plan_wide(const MmArgs& s, int T, Plan& pl) {
+    static const bool no_gemv = getenv("GGQ_NO_GEMV") != nullptr;
+    static const bool off = [] { const char* e = getenv("GGQ_WIDE"); return e && e[0] == '0'; }();   // dev: GGQ_WIDE=0
+    if (T != 1 || no_gemv || s.sync || off) return false;
+    const int64_t tiles = s.W2 ? (s.O + 7) / 8 : (s.O + 15) / 16;
+    if (tiles * (s.K / 1024) / (static_cast<int64_t>(num_sms()) * 8) < 8) return false;
+    return make_plan_cfg<1, true>(s, 1, 8, 1, false, pl) && pl.p.stages >= 2 && pl.at == 1 && pl.p.n_slices == 1;
+}
+
+template <int FMT, int NT, int AT, int NW, int MINB, bool GV = false, bool DUAL = false, bool WIDE = false>
 static int launch_kernel(const Plan& pl, cudaStream_t stream, const uint8_t* W2 = nullptr) {
-    auto kern = decode_kernel<FMT, NT, AT, NW, MINB, GV, DUAL>;
+    auto kern = decode_kernel<FMT, NT, AT, NW, MINB, GV, DUAL, WIDE>;
     static int configured_dev_mask[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -887,9 +911,16 @@ static int launch_fmt(const MmArgs& a) {
         for (int i = 0; i < a.n_out; ++i) s.C[i] = static_cast<__half*>(a.C[i]) + t0 * a.ldc;
         const int T = static_cast<int>(std::min<int64_t>(16, a.T - t0));
         Plan pl;
+        static const bool no_gemv = getenv("GGQ_NO_GEMV") != nullptr;
+        if constexpr (FMT == 1) {
+            if (make_plan_wide(s, T, pl)) {
+                const int rcw = launch_kernel<1, 1, 1, 8, 1, true, false, true>(pl, a.stream);
+                if (rcw != 0) return rcw;
+                continue;
+            }
+        }
         if (!make_plan<FMT>(s, T, pl)) return GGQ_E_FAMILY;
         int rc;
-        static const bool no_gemv = getenv("GGQ_NO_GEMV") != nullptr;
         if (T == 1 && pl.at == 1 && pl.p.n_slices == 1 && !no_gemv) {  // single token: GEMV tile code
             rc = pl.occ == 2   ? launch_kernel<FMT, 1, 1, 8, 2, true>(pl, a.stream)
                  : pl.nw == 12 ? launch_kernel<FMT, 1, 1, 12, 1, true>(pl, a.stream)
