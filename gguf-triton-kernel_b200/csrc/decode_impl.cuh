@@ -829,15 +829,14 @@ static bool make_plan(const MmArgs& a, int T, Plan& pl) {
     return make_plan_cfg<FMT>(a, T, 8, 1, true, pl);
 }
 
-// Q4_K single-token GEMV on large layers: the wide-chunk geometry (KGeo<1, true>), 8 warps x 2 stages of 9.2 KB (10 warps
-// measured slower: 53.5 vs 49.5 us on the lm_head).  Small layers (fewer than 8 wide items per warp) keep the
-// fine-grained geometry; shapes whose activations do not fit next to the wide rings fall back as well.
+// Q4_K single-token GEMV: the wide-chunk geometry (KGeo<1, true>), 8 warps x 2 stages of 9.2 KB, whenever it fits (10
+// warps measured slower: 53.5 vs 49.5 us on the lm_head).  It won on every size measured, 4096 x 4096 (6.0 -> 5.6 us) to
+// 128256 x 4096 (51.8 -> 49.4 us), gpurun_out/r2_wide.log / r2_wide2.log; shapes whose activations do not fit next to
+// the wide rings (K = 28672) fall back to the fine-grained geometry.
 static bool make_plan_wide(const MmArgs& s, int T, Plan& pl) {
     static const bool no_gemv = getenv("GGQ_NO_GEMV") != nullptr;
     static const bool off = [] { const char* e = getenv("GGQ_WIDE"); return e && e[0] == '0'; }();   // dev: GGQ_WIDE=0
-    if (T != 1 || no_gemv || s.sync || off) return false;
-    const int64_t tiles = s.W2 ? (s.O + 7) / 8 : (s.O + 15) / 16;
-    if (tiles * (s.K / 1024) / (static_cast<int64_t>(num_sms()) * 8) < 8) return false;
+    if (T != 1 || no_gemv || off) return false;
     return make_plan_cfg<1, true>(s, 1, 8, 1, false, pl) && pl.p.stages >= 2 && pl.at == 1 && pl.p.n_slices == 1;
 }
 
