@@ -47,10 +47,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory per CT
 constexpr int SMEM_LIMIT_2 = 113 * 1024;  // per CTA when two CTAs share an SM (228 KB - 2 x 1 KB reserved)
 
 // Kernel geometry = the format's tile geometry (decode_tile.cuh) with the CHUNK — what one ring stage holds of a row —
-// optionally doubled.  WIDE (Q4_K single-token GEMV on large layers): 4 blocks = 576 B per row and stage, filled by two
-// back-to-back 288 B boxes: DRAM sees 576 contiguous bytes per row and request, and the per-chunk control code runs half
-// as often (measured: lm_head 51.8 -> 49.4 us, 28672 x 8192 27.9 -> 26.5 us; with T = 8 the same geometry loses 30 %,
-// gpurun_out/r2_ab.log).  The lane-level tile code only knows PREP_BLOCKS / SLOT and is the same for both.
+// optionally doubled.  WIDE (Q4_K single-token GEMV): 4 blocks = 576 B per row and stage, filled by two back-to-back
+// 288 B boxes: the per-chunk control code (barrier wait, refill, cursor arithmetic) runs half as often — the rings alone
+// already stream at the copy peak, what the GEMV loses is instruction time (measured: lm_head 51.8 -> 49.4 us, 27.5 M ->
+// 24.5 M warp instructions; with T = 8 the same geometry loses 30 %, gpurun_out/r2_ab.log).  The lane-level tile code
+// only knows PREP_BLOCKS / SLOT and is the same for both.
 template <int FMT, bool WIDE> struct KGeo : Geo<FMT> {};
 template <> struct KGeo<1, true> : Geo<1> {
     static constexpr int CHUNK_BLOCKS = 4, CHUNK_ELEMS = 1024, CHUNK_BYTES = 576;
