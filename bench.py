@@ -398,6 +398,8 @@ def single_gpu_cells(torch, ext, hbm_peak, tf_peak, W_head):
     # configs[0] (the reference's own CPU-runnable case) and the small Llama-3-8B layers
     cells += decode_cell(torch, ext, "Q8_0 4096x4096 [configs[0]]", "q8_0", 4096, 4096, (1,), hbm_peak)
     cells += decode_cell(torch, ext, "Q4_K 14336x4096", "q4_k", 14336, 4096, (1, 16), hbm_peak)
+    cells += decode_cell(torch, ext, "Q4_K 4096x4096", "q4_k", 4096, 4096, (1,), hbm_peak)
+    cells += decode_cell(torch, ext, "Q8_0 lm_head 128256x4096", "q8_0", 128256, 4096, (1,), hbm_peak)
     cells += decode_cell(torch, ext, "Q6_K down_proj 4096x14336", "q6_k", 4096, 14336, (1,), hbm_peak)
     # configs[3] / [2]: prefill through tcgen05
     cells.append(prefill_cell(torch, ext, "Q4_K FFN 28672x8192", "q4_k", 28672, 8192, 4096, tf_peak))
