@@ -89,7 +89,8 @@ int ggq_mm_ex(int fmt, const void* W, const void* X, int64_t ldx, void* const* C
  * same format.  T <= 16 on decode-eligible shapes: ONE kernel streams both matrices once and applies the activation in
  * the accumulator registers (no intermediate [T, 2*O] in HBM).  Other shapes: gate GEMM -> workspace, up GEMM -> C,
  * one elementwise pass; that form needs `workspace_bytes` >= ggq_mm_swiglu_workspace(...) (0 when the fused kernel
- * runs; `workspace` may then be NULL).
+ * runs; `workspace` may then be NULL).  The query assumes 16-byte aligned Wg / Wu / X (what cudaMalloc and torch give);
+ * with a less aligned pointer the call takes the composed form and returns GGQ_E_POINTER if no workspace was passed.
  */
 int64_t ggq_mm_swiglu_workspace(int fmt, int64_t O, int64_t T, int64_t K);
 int ggq_mm_swiglu(int fmt, const void* Wg, const void* Wu, const void* X, void* C, int64_t O, int64_t T, int64_t K,
