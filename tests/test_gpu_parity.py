@@ -122,6 +122,25 @@ DECODE_SHAPES = [  # (M, N, K)
 ]
 
 
+@pytest.mark.parametrize("shape", [(16, 1, 256), (40, 1, 768), (40, 1, 1280), (130, 1, 2304), (300, 1, 3328), (2000, 1, 5376)])
+def test_q4_k_gemv_wide_stages_with_k_tails(ext, shape):
+    """Q4_K, one token: the wide-stage geometry (4 blocks per stage, two TMA boxes) on rows whose block count is not a
+    multiple of 4 — the last stage of a row is partly (or, for its second box, entirely) past the row end."""
+    M, N, K = shape
+    A = orc.random_blocks("q4_k", M, K, seed=K)
+    X = rand_x(N, K, M)
+    C = run_mm(ext, "q4_k", A, X, M, N, K, family=ext.FAMILY_DECODE)
+    check_tier1("q4_k", A, X, M, N, K, C, "decode wide")
+    from kernels.swiglu import mmq_swiglu
+    Au = orc.random_blocks("q4_k", M, K, seed=K + 1)
+    Xs = (X.astype(np.float32) * 0.05).astype(np.float16)
+    S = mmq_swiglu("q4_k", dev(A), dev(Au), dev(Xs), M, N, K).float().cpu().numpy()
+    g = orc.ref32("q4_k", A, Xs, M, N, K).astype(np.float16).astype(np.float32)
+    u = orc.ref32("q4_k", Au, Xs, M, N, K).astype(np.float16).astype(np.float32)
+    mx, fro = orc.tier1_errors(S, g / (1.0 + np.exp(-g)) * u)
+    assert mx <= orc.TIER1_MAX and fro <= orc.TIER1_FRO, (shape, mx, fro)
+
+
 @pytest.mark.parametrize("fmt", FMTS)
 @pytest.mark.parametrize("shape", DECODE_SHAPES)
 def test_decode_family(ext, fmt, shape):
