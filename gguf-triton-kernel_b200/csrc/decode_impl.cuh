@@ -10,8 +10,8 @@
 //     for each of my (tile, k-chunk) items:   wait(full[stage]) -> prep scales -> 16 x {8,16} MMA tile
 //                                             -> re-arm the stage with the item STAGES ahead
 //
-// A stage holds one chunk (Geo<FMT>::CHUNK_BLOCKS blocks) of each of the tile's 16 rows, copied verbatim (16-byte
-// aligned supersets where a chunk starts mid-vector, Q6_K).  Activations are staged once as raw fp16 rows by bulk
+// A stage holds one chunk (KGeo<FMT, WIDE>::CHUNK_BLOCKS blocks: the format's tile geometry, doubled for the Q4_K GEMV) of
+// each of the tile's 16 rows, copied verbatim (16-byte aligned supersets where a chunk starts mid-vector, Q6_K).  Activations are staged once as raw fp16 rows by bulk
 // copy, plus a table of per-sub-block activation sums that cancels the integer->fp16 bias (decode_tile.cuh).
 //
 // Work decomposition (static, chosen on the host, `ggq_decode_plan`):
@@ -22,9 +22,11 @@
 //     rank S-1 -> ... -> 0 through per-warp DSMEM mailboxes (st.async + mbarrier);
 //   * last resort: K-slices staged one after the other with AT = 4 live tiles per warp and KW warps per tile.
 // T == 1 uses the GEMV tile code (`GV`): the 8 MMA columns carry 8 sub-blocks instead of 8 tokens.
+// `DUAL`: fused SwiGLU up-projection, 8 gate + 8 up rows per tile (decode_dual.cu).
 // Launches use programmatic stream serialization: the prologue and the weight prefetch of a launch overlap the drain
 // of the previous kernel; `griddepcontrol.wait` sits in front of the first access to the activations.
-// With a `ggq_peer_sync` the kernel also does the N-split exchange (activation push, peer stores, epoch flags).
+// With a `ggq_peer_sync` the kernel also does the N-split exchange (activations and output tiles as flag-in-data lines
+// into peer-mapped landing buffers, bounded waits).
 // HBM traffic = packed weight bytes once (+ <= 3 % activations/outputs); roofline: HBM bandwidth.
 #pragma once
 #include <cstring>
