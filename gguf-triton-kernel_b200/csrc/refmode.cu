@@ -2,9 +2,10 @@
 // in exactly the operation order of the reference's CPU implementations, so the result equals
 // kernels/cpu_impls/mmq_*_q8_1_cpu bit for bit.  One thread per output element walks the blocks
 // sequentially — the fp16 accumulation chain of an output IS sequential in the reference — and consecutive threads own
-// consecutive weight rows of the same token.  Two kernels: `refmode_fast_kernel` (rows that are whole 32-bit words:
-// 128-bit / 32-bit vector loads, the integer block dots on DP4A, the activation block read once per warp as a broadcast)
-// and the byte-wise `refmode_kernel` for every other shape.  The integer dots are exact in any order; the floating-point
+// consecutive weight rows of the same token.  Three kernels: `refmode_tile_q4k_kernel` (Q4_K: rows staged through a
+// cp.async-filled shared-memory tile, HBM-friendly), `refmode_fast_kernel` (rows that are whole 32-bit words: 128-bit /
+// 32-bit vector loads; both with the integer block dots on DP4A and the activation block read as a broadcast) and the
+// byte-wise `refmode_kernel` for every other shape.  The integer dots are exact in any order; the floating-point
 // operations are the same explicitly rounded intrinsics in the same order in both.
 //   Q8_0  kernels/cpu_impls/mmq_q8_0_q8_1_cpu.py:37-54   r = fp16(fp16(d_w*d_x) * dot);            C = fp16(C + r)
 //   Q4_K  kernels/cpu_impls/mmq_q4_k_q8_1_cpu.py:94-117  r = ((d*sc)*d_x)*dot - (dmin*m)*s_x (fp32); C = fp16(C + fp16(r))
@@ -240,8 +241,151 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
         if (tt < nt) C[(t0 + tt) * O + o] = __float2half_rn(c[tt]);
 }
 
+// ---- Q4_K, tiled: HBM-rate form of the same arithmetic ---------------------------------------------------------------
+// One thread per weight row still (the accumulation chain of an output is sequential), but the packed rows reach the
+// threads through shared memory: the CTA's 128 threads copy a tile of 128 rows x 1 super-block (144 B per row) with
+// coalesced 16-byte cp.async into a double-buffered stage (176-byte row pitch: the threads' 128-bit reads of their own
+// row are conflict free; small stages keep four CTAs = 16 warps per SM for the single-token case, whose per-row chain of
+// dependent operations needs the warps), and the Q8_1 activations of the CTA's token tile are staged once.  Loads of the next stage
+// overlap the arithmetic of the current one, so the kernel streams the weights once at HBM rate instead of waiting on
+// every thread's own scattered 16-byte loads.
+constexpr int RT_ROWS = 128, RT_SB = 1, RT_PITCH = RT_SB * 144 + 32;   // 176 B = 11 vectors: an odd pitch, 45 KB for both stages
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TT>
+__global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t* __restrict__ W, const uint8_t* __restrict__ XQ,
+                                                                   __half* __restrict__ C, int64_t O, int64_t T, int64_t K) {
+    extern __shared__ __align__(16) uint8_t rsm[];
+    const int tid = threadIdx.x;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * RT_ROWS;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.y) * TT;
+    const int nt = static_cast<int>(T - t0 < TT ? T - t0 : TT);
+    const int nsb = static_cast<int>(K / 256);
+    const int64_t rowB = static_cast<int64_t>(nsb) * 144;
+    const int xwords = nsb * 8 * 9;                                // words per token
+    uint32_t* xs = reinterpret_cast<uint32_t*>(rsm);               // [TT][xwords]
+    uint8_t* ws = rsm + ((static_cast<size_t>(TT) * xwords * 4 + 15) & ~size_t{15});   // [2][RT_ROWS][RT_PITCH]
+    const int nstage = (nsb + RT_SB - 1) / RT_SB;
+
+    auto issue = [&](int st) {   // stage st -> buffer st & 1
+        const int sb0 = st * RT_SB;
+        const int vec_per_row = min(RT_SB, nsb - sb0) * 9;         // 16-byte pieces of this stage per row
+        uint8_t* dst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
+        for (int p = tid; p < RT_ROWS * vec_per_row; p += RT_ROWS) {
+            const int r = p / vec_per_row, c = p - r * vec_per_row;
+            const int64_t row = min(row0 + r, O - 1);              // rows past the end re-read the last row (never stored)
+            cp_async16(dst + r * RT_PITCH + c * 16, W + row * rowB + static_cast<int64_t>(sb0) * 144 + c * 16);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    {   // the token tile's activations, once (4-byte words; XQ rows are 36 * K/32 bytes: 4-byte aligned)
+        const uint32_t* xg = reinterpret_cast<const uint32_t*>(XQ) + t0 * xwords;
+        for (int i = tid; i < nt * xwords; i += RT_ROWS) xs[i] = __ldg(xg + i);
+    }
+    float c[TT];
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) c[tt] = 0.f;
+    for (int st = 0; st < nstage; ++st) {
+        if (st + 1 < nstage) {
+            issue(st + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();   // stage st (and, the first time, the activations) are visible to every thread
+        const uint8_t* mine = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH + tid * RT_PITCH;
+        const int nhere = min(RT_SB, nsb - st * RT_SB);
+        for (int u = 0; u < nhere; ++u) {
+            const int sb = st * RT_SB + u;
+            const uint4* wb = reinterpret_cast<const uint4*>(mine + u * 144);
+            const uint4 h = wb[0];
+            const float d = hlo(h.x), dmin = hhi(h.x);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+                const uint4 qa = wb[1 + 2 * pr], qb = wb[2 + 2 * pr];
+                const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int j = 2 * pr + hf;
+                    int sc, m;
+                    if (j < 4) {
+                        sc = (h.y >> (8 * j)) & 63;
+                        m = (h.z >> (8 * j)) & 63;
+                    } else {
+                        const int sh = 8 * (j - 4);
+                        sc = ((h.w >> sh) & 0x0F) | ((((h.y >> sh) & 0xFF) >> 6) << 4);
+                        m = (((h.w >> sh) & 0xFF) >> 4) | ((((h.z >> sh) & 0xFF) >> 6) << 4);
+                    }
+                    uint32_t q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = (hf ? (w[i] >> 4) : w[i]) & 0x0F0F0F0Fu;
+                    const float dsc = __fmul_rn(d, static_cast<float>(sc)), dm = __fmul_rn(dmin, static_cast<float>(m));
+#pragma unroll
+                    for (int tt = 0; tt < TT; ++tt) {
+                        if (tt >= nt) break;
+                        const uint32_t* xb = xs + tt * xwords + (sb * 8 + j) * 9;   // the same address in every thread: broadcast
+                        const uint32_t x0 = xb[0];
+                        int dot = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dot = dp4(q[i], xb[1 + i], dot);
+                        const float t1 = __fmul_rn(__fmul_rn(dsc, hlo(x0)), static_cast<float>(dot));
+                        const float t2 = __fmul_rn(dm, hhi(x0));
+                        c[tt] = acc16(c[tt], __fsub_rn(t1, t2));
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with buffer st & 1 before stage st + 2 is copied into it
+    }
+    const int64_t row = row0 + tid;
+    if (row < O) {
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt)
+            if (tt < nt) C[(t0 + tt) * O + row] = __float2half_rn(c[tt]);
+    }
+}
+
+// returns false when the shape does not fit (the activations of a token tile must fit next to the two stages)
+static bool launch_tile_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
+    // the largest token tile (8, 4, 1) whose activations fit next to the two stages with two CTAs per SM (113 KB each;
+    // one token at K = 4096: 50 KB, four CTAs per SM);
+    // a layer with more tokens than the tile streams its weights once per token tile
+    constexpr size_t LIMIT = 113 * 1024;
+    auto smem_of = [&](int t) { return ((static_cast<size_t>(t) * (K / 32) * 36 + 15) & ~size_t{15}) + 2 * static_cast<size_t>(RT_ROWS) * RT_PITCH; };
+    int tt = T == 1 ? 1 : T <= 4 ? 4 : 8;
+    while (tt > 1 && smem_of(tt) > LIMIT) tt = tt == 8 ? 4 : 1;
+    const size_t smem = smem_of(tt);
+    if (smem > LIMIT || (O + RT_ROWS - 1) / RT_ROWS > 0x7fffffff || (T + tt - 1) / tt > 65535) return false;
+    const dim3 grid(static_cast<unsigned>((O + RT_ROWS - 1) / RT_ROWS), static_cast<unsigned>((T + tt - 1) / tt));
+    auto go = [&](auto kern) {
+        static bool configured[3][64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int slot = tt == 1 ? 0 : tt == 4 ? 1 : 2;
+        if (dev >= 0 && dev < 64 && !configured[slot][dev]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(LIMIT));
+            configured[slot][dev] = true;
+        }
+        kern<<<grid, RT_ROWS, smem, s>>>(w, x, c, O, T, K);
+    };
+    if (tt == 1) go(refmode_tile_q4k_kernel<1>);
+    else if (tt == 4) go(refmode_tile_q4k_kernel<4>);
+    else go(refmode_tile_q4k_kernel<8>);
+    return true;
+}
+
 template <int FMT>
 static void launch_fast(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
+    if (FMT == GGQ_Q4_K) {
+        static const bool no_tile = getenv("GGQ_REFMODE_NOTILE") != nullptr;   // dev: the untiled vector kernel
+        if (!no_tile && launch_tile_q4k(w, x, c, O, T, K, s)) return;
+    }
     auto grid = [&](int tt) { return static_cast<unsigned>((O * ((T + tt - 1) / tt) + 127) / 128); };
     if (T == 1) refmode_fast_kernel<FMT, 1><<<grid(1), 128, 0, s>>>(w, x, c, O, T, K);
     else if (T <= 4) refmode_fast_kernel<FMT, 4><<<grid(4), 128, 0, s>>>(w, x, c, O, T, K);

@@ -213,7 +213,8 @@ int ggq_dequant_q6_k_f32(const void* W, void* out, int64_t O, int64_t K, void* s
  * ggq_quantize_q8_1_f16); integer block dots and fp16 accumulation in the exact operation order of
  * kernels/cpu_impls/mmq_{q8_0,q4_k,q6_k}_q8_1_cpu.py, so C[T, O] equals their result bit for bit.  One thread per weight
  * row (the fp16 accumulation chain of an output is sequential in the reference), vector loads and DP4A block dots when
- * the rows are whole 32-bit words (Q4_K always; Q8_0 / Q6_K: an even number of blocks per row), byte-wise otherwise.
+ * the rows are whole 32-bit words (Q4_K always — through a cp.async-filled shared-memory tile; Q8_0 / Q6_K: an even
+ * number of blocks per row), byte-wise otherwise.
  * For callers that want the reference's own numbers: its int8 activation noise (~5e-3) is outside the tolerance the
  * fp16-activation entry points above are held to.
  */
