@@ -171,3 +171,35 @@ def test_dequant_rejects_rows_beyond_32_bit_indexing():
     one = ctypes.c_void_p(256)
     assert L.ggq_dequant_q4_k_f16(one, one, 1, (1 << 31), None) == -1
     assert L.ggq_dequant_q8_0_f16(one, one, 1, (1 << 30) + 32, None) == -1
+
+
+def test_describe_and_push_columns_host_side():
+    """ggq_describe names the kernel AUTO dispatch would launch (bench.py `roofline.kernel`); ggq_push_columns validates its
+    arguments before touching the GPU."""
+    from kernels import _ext
+    L = _ext.lib()
+    I64, P, INT = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+    L.ggq_describe.argtypes = [INT, I64, I64, I64, ctypes.c_char_p, INT]
+    L.ggq_describe.restype = INT
+    buf = ctypes.create_string_buffer(256)
+
+    def d(f, o, t, k):
+        assert L.ggq_describe(f, o, t, k, buf, 256) == 0
+        return buf.value.decode()
+    assert "decode_kernel<Q4_K" in d(1, 128256, 1, 4096) and "WIDE" in d(1, 128256, 1, 4096)   # the headline kernel
+    assert "WIDE" not in d(1, 128256, 8, 4096) and "WIDE" not in d(2, 128256, 1, 4096)          # Q4_K single token only
+    assert "WIDE" not in d(1, 8192, 1, 28672)                    # activations do not fit next to the wide rings
+    assert "skinny_kernel<Q8_0,N=16" in d(0, 28672, 16, 8192)
+    assert "prefill2_kernel<Q6_K>" in d(2, 128256, 2048, 4096)
+    assert "generic_kernel" in d(0, 8, 1, 32)
+    assert L.ggq_describe(1, 4096, 1, 100, buf, 256) == -1 and L.ggq_describe(9, 4096, 1, 256, buf, 256) == -4
+    L.ggq_push_columns.argtypes = [P, ctypes.POINTER(P), INT, I64, I64, I64, P]
+    L.ggq_push_columns.restype = INT
+    one = P(256)
+    dst = (P * 2)(256, 512)
+    assert L.ggq_push_columns(one, dst, 0, 64, 32, 4, None) == 0          # no peers: nothing to do
+    assert L.ggq_push_columns(one, dst, 2, 16, 32, 4, None) == -1         # width beyond the pitch
+    assert L.ggq_push_columns(one, dst, 9, 64, 32, 4, None) == -1         # more than 8 peers
+    assert L.ggq_push_columns(None, dst, 2, 64, 32, 4, None) == -2
+    bad = (P * 2)(256, None)
+    assert L.ggq_push_columns(one, bad, 2, 64, 32, 4, None) == -2
