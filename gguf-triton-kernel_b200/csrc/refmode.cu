@@ -272,15 +272,22 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
     uint8_t* ws = rsm + ((static_cast<size_t>(TT) * xwords * 4 + 15) & ~size_t{15});   // [2][RT_ROWS][RT_PITCH]
     const int nstage = (nsb + RT_SB - 1) / RT_SB;
 
-    auto issue = [&](int st) {   // stage st -> buffer st & 1
-        const int sb0 = st * RT_SB;
-        const int vec_per_row = min(RT_SB, nsb - sb0) * 9;         // 16-byte pieces of this stage per row
+    // the 16-byte pieces this thread copies per stage (128 rows x 9 pieces, piece p = tid + 128 j: consecutive threads copy
+    // consecutive pieces of a row) are the same in every stage: source row / destination offset are computed once
+    static_assert(RT_SB == 1, "one super-block (9 vectors) per row and stage");
+    const uint8_t* src[9];
+    uint32_t dsto[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int p = tid + RT_ROWS * j, r = p / 9, c = p - 9 * r;
+        const int64_t row = min(row0 + r, O - 1);                  // rows past the end re-read the last row (never stored)
+        src[j] = W + row * rowB + c * 16;
+        dsto[j] = static_cast<uint32_t>(r * RT_PITCH + c * 16);
+    }
+    auto issue = [&](int st) {   // stage st (super-block st) -> buffer st & 1
         uint8_t* dst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
-        for (int p = tid; p < RT_ROWS * vec_per_row; p += RT_ROWS) {
-            const int r = p / vec_per_row, c = p - r * vec_per_row;
-            const int64_t row = min(row0 + r, O - 1);              // rows past the end re-read the last row (never stored)
-            cp_async16(dst + r * RT_PITCH + c * 16, W + row * rowB + static_cast<int64_t>(sb0) * 144 + c * 16);
-        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) cp_async16(dst + dsto[j], src[j] + static_cast<int64_t>(st) * 144);
         cp_async_commit();
     };
     issue(0);
