@@ -386,7 +386,7 @@ def q8_1_cell(torch, ext, name, fmt, o, k, t, hbm_peak, W):
     gbs = nbytes / (ms * 1e-3) / 1e9
     del W2
     torch.cuda.empty_cache()
-    return {"cell": f"q8_1-mode {name} T={t}", "family": "reference arithmetic (Q8_1 activations, DP4A block dots, fp16 accumulator)",
+    return {"cell": f"q8_1-mode {name} T={t}", "family": "reference arithmetic (Q8_1 activations, integer block dots: DP4A at T <= 2, tensor-core IMMA beyond; fp16 accumulator)",
             "fmt": fmt, "O": o, "K": k, "T": t, "us": round(ms * 1e3, 2), "achieved": round(gbs, 1), "unit": "GB/s",
             "peak": hbm_peak, "frac": round(gbs / hbm_peak, 3), "frac_8TBps": round(gbs / 8000.0, 3),
             "parity": {"bit_identical_to_cpu_impls_port": same, "rows_sampled": int(len(pick)), "ok": same}}

@@ -2,7 +2,9 @@
 // in exactly the operation order of the reference's CPU implementations, so the result equals
 // kernels/cpu_impls/mmq_*_q8_1_cpu bit for bit.  One thread per output element walks the blocks
 // sequentially — the fp16 accumulation chain of an output IS sequential in the reference — and consecutive threads own
-// consecutive weight rows of the same token.  Three kernels: `refmode_tile_q4k_kernel` (Q4_K: rows staged through a
+// consecutive weight rows of the same token.  Four kernels: `refmode_mma_q4k_kernel` (Q4_K, T >= 3: the block dots of
+// 16 rows x 8 tokens by one integer tensor-core MMA, the chains in the accumulator-fragment layout),
+// `refmode_tile_q4k_kernel` (Q4_K: rows staged through a
 // cp.async-filled shared-memory tile, HBM-friendly), `refmode_fast_kernel` (rows that are whole 32-bit words: 128-bit /
 // 32-bit vector loads; both with the integer block dots on DP4A and the activation block read as a broadcast) and the
 // byte-wise `refmode_kernel` for every other shape.  The integer dots are exact in any order; the floating-point
@@ -87,6 +89,11 @@ __global__ void __launch_bounds__(128) refmode_kernel(const uint8_t* __restrict_
 }
 
 // ---- vectorised form -----------------------------------------------------------------------------------------------
+// The accumulator of the vectorised kernels is kept in fp16 and advanced with ONE half-precision add: fp16(fp32(c + r16))
+// — what torch's CPU kernel and the byte-wise kernel above compute — equals the correctly rounded fp16 sum, because a
+// second rounding from a format of P >= 2p + 2 significand bits (24 >= 2 * 11 + 2) is innocuous for +, -, *, / (Figueroa).
+// __hadd_rn / __hadd2_rn are never contracted into an FMA.
+__device__ __forceinline__ __half acc16h(__half c, float r32) { return __hadd_rn(c, __float2half_rn(r32)); }
 __device__ __forceinline__ float hlo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu))); }
 __device__ __forceinline__ float hhi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return __dp4a(static_cast<int>(a), static_cast<int>(b), c); }
@@ -123,9 +130,9 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
     const int64_t nb32 = K / 32;
     const int64_t xstride = nb32 * 9;                                               // words per token
     const uint32_t* xrow = reinterpret_cast<const uint32_t*>(XQ) + t0 * xstride;    // 9 words per Q8_1 block: {d, s}, qs[32]
-    float c[TT];
+    __half c[TT];
 #pragma unroll
-    for (int tt = 0; tt < TT; ++tt) c[tt] = 0.f;
+    for (int tt = 0; tt < TT; ++tt) c[tt] = __ushort_as_half(0);
     if (FMT == GGQ_Q8_0) {
         const uint32_t* wrow = reinterpret_cast<const uint32_t*>(W + o * nb32 * 34);
         for (int64_t b = 0; b < nb32; b += 2) {   // two blocks = 68 bytes = 17 words
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dot = dp4(q[half][i], __ldg(xb + 1 + i), dot);
                     const float sc = __half2float(__float2half_rn(__fmul_rn(dw[half], hlo(x0))));  // fp16 * fp16 -> fp16
-                    c[tt] = acc16(c[tt], __fmul_rn(sc, static_cast<float>(dot)));
+                    c[tt] = acc16h(c[tt], __fmul_rn(sc, static_cast<float>(dot)));
                 }
             }
         }
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
                         for (int i = 0; i < 8; ++i) dot = dp4(q[i], __ldg(xb + 1 + i), dot);
                         const float t1 = __fmul_rn(__fmul_rn(dsc, hlo(x0)), static_cast<float>(dot));
                         const float t2 = __fmul_rn(dm, hhi(x0));
-                        c[tt] = acc16(c[tt], __fsub_rn(t1, t2));
+                        c[tt] = acc16h(c[tt], __fsub_rn(t1, t2));
                     }
                 }
             }
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
                             dot2 = dp4(q[4 + i], __ldg(xb + 5 + i), dot2);
                         }
                         const float inner = __fadd_rn(__fmul_rn(s1, static_cast<float>(dot1)), __fmul_rn(s2f, static_cast<float>(dot2)));
-                        c[tt] = acc16(c[tt], __fmul_rn(hlo(x0), inner));
+                        c[tt] = acc16h(c[tt], __fmul_rn(hlo(x0), inner));
                     }
                 }
             }
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
     }
 #pragma unroll
     for (int tt = 0; tt < TT; ++tt)
-        if (tt < nt) C[(t0 + tt) * O + o] = __float2half_rn(c[tt]);
+        if (tt < nt) C[(t0 + tt) * O + o] = c[tt];
 }
 
 // ---- Q4_K, tiled: HBM-rate form of the same arithmetic ---------------------------------------------------------------
@@ -291,13 +298,19 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
         cp_async_commit();
     };
     issue(0);
-    {   // the token tile's activations, once (4-byte words; XQ rows are 36 * K/32 bytes: 4-byte aligned)
+    const int nblk = nsb * 8;
+    {   // the token tile's activations, once (XQ rows are 36 * K/32 bytes: 4-byte aligned), regrouped per token as
+        // {d, s} words of all blocks, then the blocks' 8 quant words at 32-byte aligned offsets: a thread reads a block
+        // with two 128-bit broadcast loads and one 32-bit load instead of nine 32-bit loads
         const uint32_t* xg = reinterpret_cast<const uint32_t*>(XQ) + t0 * xwords;
-        for (int i = tid; i < nt * xwords; i += RT_ROWS) xs[i] = __ldg(xg + i);
+        for (int i = tid; i < nt * xwords; i += RT_ROWS) {
+            const int tt = i / xwords, r = i - tt * xwords, b = r / 9, w = r - 9 * b;
+            xs[tt * xwords + (w == 0 ? b : nblk + 8 * b + w - 1)] = __ldg(xg + i);
+        }
     }
-    float c[TT];
+    __half c[TT];
 #pragma unroll
-    for (int tt = 0; tt < TT; ++tt) c[tt] = 0.f;
+    for (int tt = 0; tt < TT; ++tt) c[tt] = __ushort_as_half(0);
     for (int st = 0; st < nstage; ++st) {
         if (st + 1 < nstage) {
             issue(st + 1);
@@ -336,14 +349,17 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
 #pragma unroll
                     for (int tt = 0; tt < TT; ++tt) {
                         if (tt >= nt) break;
-                        const uint32_t* xb = xs + tt * xwords + (sb * 8 + j) * 9;   // the same address in every thread: broadcast
-                        const uint32_t x0 = xb[0];
+                        const uint32_t* xt = xs + tt * xwords;                      // the same addresses in every thread: broadcast
+                        const uint32_t x0 = xt[sb * 8 + j];
+                        const uint4 xa = *reinterpret_cast<const uint4*>(xt + nblk + 8 * (sb * 8 + j));
+                        const uint4 xb = *reinterpret_cast<const uint4*>(xt + nblk + 8 * (sb * 8 + j) + 4);
+                        const uint32_t xq[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                         int dot = 0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dot = dp4(q[i], xb[1 + i], dot);
+                        for (int i = 0; i < 8; ++i) dot = dp4(q[i], xq[i], dot);
                         const float t1 = __fmul_rn(__fmul_rn(dsc, hlo(x0)), static_cast<float>(dot));
                         const float t2 = __fmul_rn(dm, hhi(x0));
-                        c[tt] = acc16(c[tt], __fsub_rn(t1, t2));
+                        c[tt] = acc16h(c[tt], __fsub_rn(t1, t2));
                     }
                 }
             }
@@ -354,8 +370,164 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
     if (row < O) {
 #pragma unroll
         for (int tt = 0; tt < TT; ++tt)
-            if (tt < nt) C[(t0 + tt) * O + row] = __float2half_rn(c[tt]);
+            if (tt < nt) C[(t0 + tt) * O + row] = c[tt];
     }
+}
+
+// ---- Q4_K, two or more tokens: the integer block dots on the tensor cores ---------------------------------------------
+// For T >= 2 the thread-per-row form above spends its time in the per-token work of every sub-block (nine activation
+// loads and eight DP4A for each 32-element dot).  Here a warp owns 32 weight rows and a tile of 8 tokens, and one
+// mma.sync.m16n8k32 (s8 x s8 -> s32; nibbles 0..15 and Q8_1 quants are exact int8 operands, a 32-element sum of
+// products is exact in int32) delivers the 16 x 8 dots of a sub-block: a thread then holds the dots of rows g, g + 8 and
+// tokens 2 tg, 2 tg + 1 (g = lane / 4, tg = lane % 4) and runs those four outputs' floating-point chains — the same
+// explicitly rounded operations in the same order, the two tokens of a row as one fp16x2 add.  The stage pipeline is the
+// tile kernel's (128 rows x 1 super-block by cp.async, double buffered); the 8 tokens' Q8_1 blocks of the super-block
+// travel with the stage (288 B per token, token pitch 400 B: B-fragment loads of the 8 tokens hit distinct banks), so the
+// shared-memory footprint does not depend on K and four CTAs stay resident.  d*sc and dmin*m of a (row, sub-block) are
+// computed once by the lane that owns the row (lane l <-> row 32 warp + l) and handed to the lanes that need them by
+// warp shuffles.  Requirements (checked by the launcher): W and XQ 16-byte aligned.
+constexpr int RM_TOK = 8, RM_XPITCH = 100;   // words per token and stage: 72 + 28, = 4 (mod 32)
+__device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+__global__ void __launch_bounds__(RT_ROWS) refmode_mma_q4k_kernel(const uint8_t* __restrict__ W, const uint8_t* __restrict__ XQ,
+                                                                  __half* __restrict__ C, int64_t O, int64_t T, int64_t K) {
+    extern __shared__ __align__(16) uint8_t rsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * RT_ROWS;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.y) * RM_TOK;
+    const int nt = static_cast<int>(T - t0 < RM_TOK ? T - t0 : RM_TOK);
+    const int nsb = static_cast<int>(K / 256);
+    const int64_t rowB = static_cast<int64_t>(nsb) * 144;
+    const int64_t xrowB = static_cast<int64_t>(nsb) * 288;        // bytes of one token's Q8_1 row
+    uint8_t* ws = rsm;                                                                   // [2][RT_ROWS][RT_PITCH]
+    uint8_t* xs = rsm + 2 * RT_ROWS * RT_PITCH;                                          // [2][RM_TOK][RM_XPITCH words]
+
+    // copy plan of a stage, the same in every stage: 9 weight pieces per thread (as in the tile kernel) and the
+    // 8 tokens x 18 activation pieces over the first 144 piece slots (tokens past the end re-read the last token)
+    const uint8_t* src[9];
+    uint32_t dsto[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int p = tid + RT_ROWS * j, r = p / 9, c = p - 9 * r;
+        const int64_t row = min(row0 + r, O - 1);
+        src[j] = W + row * rowB + c * 16;
+        dsto[j] = static_cast<uint32_t>(r * RT_PITCH + c * 16);
+    }
+    const uint8_t* xsrc[2];
+    uint32_t xdst[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int p = min(tid + RT_ROWS * j, RM_TOK * 18 - 1), tk = p / 18, c = p - 18 * tk;
+        xsrc[j] = XQ + (t0 + min(tk, nt - 1)) * xrowB + c * 16;
+        xdst[j] = static_cast<uint32_t>(tk * (RM_XPITCH * 4) + c * 16);
+    }
+    auto issue = [&](int st) {   // super-block st -> buffer st & 1
+        uint8_t* dst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
+        uint8_t* xd = xs + static_cast<size_t>(st & 1) * RM_TOK * RM_XPITCH * 4;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) cp_async16(dst + dsto[j], src[j] + static_cast<int64_t>(st) * 144);
+        cp_async16(xd + xdst[0], xsrc[0] + static_cast<int64_t>(st) * 288);
+        if (tid < RM_TOK * 18 - RT_ROWS) cp_async16(xd + xdst[1], xsrc[1] + static_cast<int64_t>(st) * 288);
+        cp_async_commit();
+    };
+    issue(0);
+    __half2 acc[2][2];   // [16-row tile of the warp][row g / row g + 8] = tokens (2 tg, 2 tg + 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i >> 1][i & 1] = __half2half2(__ushort_as_half(0));
+    for (int st = 0; st < nsb; ++st) {
+        if (st + 1 < nsb) {
+            issue(st + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();   // stage st is visible to every thread
+        const uint8_t* wst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
+        const uint32_t* xst = reinterpret_cast<const uint32_t*>(xs + static_cast<size_t>(st & 1) * RM_TOK * RM_XPITCH * 4);
+        // this lane's own row (row tid of the tile): d * sc and dmin * m of the 8 sub-blocks
+        float dsc[8], dm[8];
+        {
+            const uint4 h = *reinterpret_cast<const uint4*>(wst + tid * RT_PITCH);
+            const float d = hlo(h.x), dmin = hhi(h.x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int sc, m;   // q4_k_ref.c:174-186, from the header words h.y = s[0..3], h.z = s[4..7], h.w = s[8..11]
+                if (j < 4) {
+                    sc = (h.y >> (8 * j)) & 63;
+                    m = (h.z >> (8 * j)) & 63;
+                } else {
+                    const int sh = 8 * (j - 4);
+                    sc = ((h.w >> sh) & 0x0F) | ((((h.y >> sh) & 0xFF) >> 6) << 4);
+                    m = (((h.w >> sh) & 0xFF) >> 4) | ((((h.z >> sh) & 0xFF) >> 6) << 4);
+                }
+                dsc[j] = __fmul_rn(d, static_cast<float>(sc));
+                dm[j] = __fmul_rn(dmin, static_cast<float>(m));
+            }
+        }
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {   // sub-blocks 2 pr (low nibbles) and 2 pr + 1 (high nibbles) share 32 bytes
+            uint32_t wq[2][4];             // [16-row tile][row g: words tg, 4 + tg; row g + 8: words tg, 4 + tg]
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t* wr = reinterpret_cast<const uint32_t*>(wst + (32 * warp + 16 * mt + g) * RT_PITCH) + 4 + 8 * pr;
+                wq[mt][0] = wr[tg];
+                wq[mt][1] = wr[4 + tg];
+                wq[mt][2] = wr[8 * (RT_PITCH / 4) + tg];
+                wq[mt][3] = wr[8 * (RT_PITCH / 4) + 4 + tg];
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int j = 2 * pr + hf;
+                const uint32_t* xb = xst + g * RM_XPITCH + j * 9;          // B fragment: token g, bytes 4 tg.. and 16 + 4 tg..
+                const uint32_t b0 = xb[1 + tg], b1 = xb[5 + tg];
+                const uint32_t xw0 = xst[(2 * tg) * RM_XPITCH + j * 9], xw1 = xst[(2 * tg + 1) * RM_XPITCH + j * 9];
+                const float dx0 = hlo(xw0), sx0 = hhi(xw0), dx1 = hlo(xw1), sx1 = hhi(xw1);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    int dot[4];            // (row g, token 2 tg), (g, 2 tg + 1), (g + 8, 2 tg), (g + 8, 2 tg + 1)
+                    mma_s8(dot, (wq[mt][0] >> (4 * hf)) & 0x0F0F0F0Fu, (wq[mt][2] >> (4 * hf)) & 0x0F0F0F0Fu,
+                           (wq[mt][1] >> (4 * hf)) & 0x0F0F0F0Fu, (wq[mt][3] >> (4 * hf)) & 0x0F0F0F0Fu, b0, b1);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int owner = 16 * mt + 8 * rr + g;            // the lane that holds this row's scales
+                        const float ds = __shfl_sync(0xffffffffu, dsc[j], owner), dmn = __shfl_sync(0xffffffffu, dm[j], owner);
+                        const float r0 = __fsub_rn(__fmul_rn(__fmul_rn(ds, dx0), static_cast<float>(dot[2 * rr])), __fmul_rn(dmn, sx0));
+                        const float r1 = __fsub_rn(__fmul_rn(__fmul_rn(ds, dx1), static_cast<float>(dot[2 * rr + 1])), __fmul_rn(dmn, sx1));
+                        acc[mt][rr] = __hadd2_rn(acc[mt][rr], __floats2half2_rn(r0, r1));
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with buffer st & 1 before stage st + 2 is copied into it
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int64_t row = row0 + 32 * warp + 16 * mt + 8 * rr + g;
+            if (row >= O) continue;
+            if (2 * tg < nt) C[(t0 + 2 * tg) * O + row] = __low2half(acc[mt][rr]);
+            if (2 * tg + 1 < nt) C[(t0 + 2 * tg + 1) * O + row] = __high2half(acc[mt][rr]);
+        }
+}
+
+static bool launch_mma_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
+    constexpr int SMEM = 2 * RT_ROWS * RT_PITCH + 2 * RM_TOK * RM_XPITCH * 4;   // 51456 B: four CTAs per SM
+    const int64_t gx = (O + RT_ROWS - 1) / RT_ROWS, gy = (T + RM_TOK - 1) / RM_TOK;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || gx > 0x7fffffff || gy > 65535) return false;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(refmode_mma_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        configured[dev] = true;
+    }
+    refmode_mma_q4k_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), RT_ROWS, SMEM, s>>>(w, x, c, O, T, K);
+    return true;
 }
 
 // returns false when the shape does not fit (the activations of a token tile must fit next to the two stages)
@@ -391,6 +563,8 @@ template <int FMT>
 static void launch_fast(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
     if (FMT == GGQ_Q4_K) {
         static const bool no_tile = getenv("GGQ_REFMODE_NOTILE") != nullptr;   // dev: the untiled vector kernel
+        static const int mma_min_t = getenv("GGQ_REFMODE_MMA_MIN_T") ? atoi(getenv("GGQ_REFMODE_MMA_MIN_T")) : 3;   // T = 2 measured equal (96 vs 103 us on the lm_head); dev: A/B
+        if (!no_tile && T >= mma_min_t && launch_mma_q4k(w, x, c, O, T, K, s)) return;
         if (!no_tile && launch_tile_q4k(w, x, c, O, T, K, s)) return;
     }
     auto grid = [&](int tt) { return static_cast<unsigned>((O * ((T + tt - 1) / tt) + 127) / 128); };

@@ -244,7 +244,9 @@ class NSplitLinear:
         return 0 if self.group is dist.group.WORLD else dist.get_global_rank(self.group, 0)
 
     def last_output(self, T: int) -> torch.Tensor:
-        return self._out[self._epoch & 1, :T]
+        """The [T, O] result of the most recent fused step (a T > 16 GEMM step writes buffer 0, a decode step the buffer of
+        its epoch's parity)."""
+        return self._out[0 if self._after_gemm else self._epoch & 1, :T]
 
     def forward(self, X, *, broadcast: bool = True, T: int | None = None) -> torch.Tensor:
         """X: fp16 [T, K] (valid on rank 0 when `broadcast`; None + T = the activations were written into

@@ -81,11 +81,13 @@ def test_reference_arithmetic_mode_is_bit_identical(golden, fmt):
 
 
 @pytest.mark.parametrize("fmt", ("q8_0", "q4_k", "q6_k"))
-@pytest.mark.parametrize("M,N,K", [(300, 3, 4096), (33, 1, 512), (70, 2, 768), (16, 17, 1280)])
+@pytest.mark.parametrize("M,N,K", [(300, 3, 4096), (33, 1, 512), (70, 2, 768), (16, 17, 1280),
+                                   (257, 8, 1024), (130, 9, 256), (128, 16, 2048)])
 def test_reference_arithmetic_mode_both_kernels(fmt, M, N, K):
     """The vectorised kernel (rows that are whole words: K/QK even, always for Q4_K) and the byte-wise one (K = 768, 1280:
     odd block counts for Q6_K / Q4_K-sized super-blocks) are both bit-identical to the oracle's kernels/cpu_impls port;
-    M not a multiple of 32 mixes tokens inside a warp."""
+    M not a multiple of 32 mixes tokens inside a warp.  Q4_K with N >= 2 runs the tensor-core (IMMA) kernel: 8-token tiles
+    (N = 9, 17: a last tile of one token; N = 3, 5: a partial tile), row tiles with a ragged end, a single-stage K = 256."""
     from kernels import q8_1_mode
     from utils.quantize.q8_1 import quantize_to_q8_1
     fn = {"q8_0": q8_1_mode.mmq_q8_0_q8_1, "q4_k": q8_1_mode.mmq_q4_k_q8_1, "q6_k": q8_1_mode.mmq_q6_k_q8_1}[fmt]
@@ -95,6 +97,29 @@ def test_reference_arithmetic_mode_both_kernels(fmt, M, N, K):
     got = fn(torch.from_numpy(A).cuda(), Bq, M, N, K).cpu().numpy()
     want = np.ascontiguousarray(orc.mmq_cpu(fmt, A, X, M, N, K))
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (fmt, M, N, K)
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 2, 1024), (140, 4, 512), (129, 8, 2048), (64, 11, 768)])
+def test_reference_arithmetic_mode_q4k_fallback_kernels(M, N, K):
+    """Q4_K kernel selection depends on pointer alignment: Q8_1 activations that are only 4-byte aligned take the
+    thread-per-row tile kernel (token tiles of 4 / 8) instead of the tensor-core one, weights that are not 16-byte aligned
+    the byte-wise kernel.  All of them are bit-identical to the oracle's port of kernels/cpu_impls."""
+    from kernels import q8_1_mode
+    from utils.quantize.q8_1 import quantize_to_q8_1
+    A = orc.random_blocks("q4_k", M, K, seed=3 * M + N)
+    X = np.random.default_rng(K + N).standard_normal((N, K)).astype(np.float16)
+    want = np.ascontiguousarray(orc.mmq_cpu("q4_k", A, X, M, N, K)).view(np.uint16)
+    Ag = torch.from_numpy(A).cuda()
+    Bq = quantize_to_q8_1(torch.from_numpy(X).cuda()).reshape(-1)
+    for a_off, b_off in ((0, 0), (0, 4), (0, 8), (2, 0)):
+        Abuf = torch.empty(Ag.numel() + 16, dtype=torch.int8, device="cuda")
+        Bbuf = torch.empty(Bq.numel() + 16, dtype=torch.int8, device="cuda")
+        Av, Bv = Abuf[a_off:a_off + Ag.numel()], Bbuf[b_off:b_off + Bq.numel()]
+        Av.copy_(Ag.reshape(-1))
+        Bv.copy_(Bq)
+        assert Av.data_ptr() % 16 == a_off and Bv.data_ptr() % 16 == b_off
+        got = q8_1_mode.mmq_q4_k_q8_1(Av, Bv, M, N, K).cpu().numpy()
+        assert np.array_equal(got.view(np.uint16), want), (M, N, K, a_off, b_off)
 
 
 def _kq_cases():
