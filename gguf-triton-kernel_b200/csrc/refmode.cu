@@ -97,6 +97,11 @@ __device__ __forceinline__ __half acc16h(__half c, float r32) { return __hadd_rn
 __device__ __forceinline__ float hlo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu))); }
 __device__ __forceinline__ float hhi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
 __device__ __forceinline__ int dp4(uint32_t a, uint32_t b, int c) { return __dp4a(static_cast<int>(a), static_cast<int>(b), c); }
+__device__ __forceinline__ int dp4_us(uint32_t a, uint32_t b, int c) {   // unsigned bytes of a x signed bytes of b
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 // n + 1 words from the 4-byte aligned address at or 2 bytes below p, shifted so that out[i] = the word at p + 4 i
 template <int N>
 __device__ __forceinline__ void ld_words(const uint8_t* p, uint32_t (&out)[N]) {
@@ -261,6 +266,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_shared, const void* src) {   // destination as a shared-space address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+// The copy plan of a stage (source pointer and shared-memory address of each 16-byte piece a thread copies) is kept as
+// LOOP-CARRIED state — sources advance by one super-block, destinations hop between the two buffers by +/- one buffer
+// size — because ptxas otherwise re-derives a loop-invariant plan inside the stage loop (division by 9, two multiplies
+// and 64-bit address assembly per piece: ~110 of the ~450 instructions per stage and thread) instead of holding it.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -274,38 +286,52 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
     const int nt = static_cast<int>(T - t0 < TT ? T - t0 : TT);
     const int nsb = static_cast<int>(K / 256);
     const int64_t rowB = static_cast<int64_t>(nsb) * 144;
-    const int xwords = nsb * 8 * 9;                                // words per token
-    uint32_t* xs = reinterpret_cast<uint32_t*>(rsm);               // [TT][xwords]
-    uint8_t* ws = rsm + ((static_cast<size_t>(TT) * xwords * 4 + 15) & ~size_t{15});   // [2][RT_ROWS][RT_PITCH]
+    const int xwords = nsb * 8 * 9;                                // words per token in XQ
+    const int xsw = nsb * 8 * 10;                                  // words per token in shared memory (d, s as two fp32)
+    uint32_t* xs = reinterpret_cast<uint32_t*>(rsm);               // [TT][xsw]
+    uint8_t* ws = rsm + static_cast<size_t>(TT) * xsw * 4;         // [2][RT_ROWS][RT_PITCH] (xsw * 4 is a multiple of 16)
     const int nstage = (nsb + RT_SB - 1) / RT_SB;
 
     // the 16-byte pieces this thread copies per stage (128 rows x 9 pieces, piece p = tid + 128 j: consecutive threads copy
     // consecutive pieces of a row) are the same in every stage: source row / destination offset are computed once
     static_assert(RT_SB == 1, "one super-block (9 vectors) per row and stage");
-    const uint8_t* src[9];
-    uint32_t dsto[9];
+    const uint8_t* src[9];   // advanced by one super-block per issued stage
+    uint32_t dsto[9];        // shared-space address of the piece in the buffer of the next stage
+    const uint32_t ws_s = static_cast<uint32_t>(__cvta_generic_to_shared(ws));
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
         const int p = tid + RT_ROWS * j, r = p / 9, c = p - 9 * r;
         const int64_t row = min(row0 + r, O - 1);                  // rows past the end re-read the last row (never stored)
         src[j] = W + row * rowB + c * 16;
-        dsto[j] = static_cast<uint32_t>(r * RT_PITCH + c * 16);
+        dsto[j] = ws_s + static_cast<uint32_t>(r * RT_PITCH + c * 16);
     }
-    auto issue = [&](int st) {   // stage st (super-block st) -> buffer st & 1
-        uint8_t* dst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
+    int bstep = RT_ROWS * RT_PITCH;   // to the other buffer
+    auto issue = [&](int) {   // the next stage (super-block st) -> buffer st & 1; called once per stage, in order
 #pragma unroll
-        for (int j = 0; j < 9; ++j) cp_async16(dst + dsto[j], src[j] + static_cast<int64_t>(st) * 144);
+        for (int j = 0; j < 9; ++j) {
+            cp_async16_s(dsto[j], src[j]);
+            src[j] += 144;
+            dsto[j] += bstep;
+        }
+        bstep = -bstep;
         cp_async_commit();
     };
     issue(0);
     const int nblk = nsb * 8;
     {   // the token tile's activations, once (XQ rows are 36 * K/32 bytes: 4-byte aligned), regrouped per token as
-        // {d, s} words of all blocks, then the blocks' 8 quant words at 32-byte aligned offsets: a thread reads a block
-        // with two 128-bit broadcast loads and one 32-bit load instead of nine 32-bit loads
+        // (d, s) of all blocks converted to fp32 (exact), then the blocks' 8 quant words at 32-byte aligned offsets: a
+        // thread reads a block with two 128-bit and one 64-bit broadcast load instead of nine 32-bit loads + 2 converts
         const uint32_t* xg = reinterpret_cast<const uint32_t*>(XQ) + t0 * xwords;
-        for (int i = tid; i < nt * xwords; i += RT_ROWS) {
-            const int tt = i / xwords, r = i - tt * xwords, b = r / 9, w = r - 9 * b;
-            xs[tt * xwords + (w == 0 ? b : nblk + 8 * b + w - 1)] = __ldg(xg + i);
+        for (int bi = tid; bi < nt * nblk; bi += RT_ROWS) {            // one Q8_1 block (9 words) per thread and turn
+            const int tt = TT == 1 ? 0 : bi / nblk, b = bi - tt * nblk;
+            const uint32_t* g = xg + static_cast<int64_t>(tt) * xwords + 9 * b;
+            uint32_t v[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __ldg(g + i);
+            uint32_t* xt = xs + tt * xsw;
+            *reinterpret_cast<float2*>(xt + 2 * b) = make_float2(hlo(v[0]), hhi(v[0]));
+            *reinterpret_cast<uint4*>(xt + 2 * nblk + 8 * b) = make_uint4(v[1], v[2], v[3], v[4]);
+            *reinterpret_cast<uint4*>(xt + 2 * nblk + 8 * b + 4) = make_uint4(v[5], v[6], v[7], v[8]);
         }
     }
     __half c[TT];
@@ -342,23 +368,26 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t
                         sc = ((h.w >> sh) & 0x0F) | ((((h.y >> sh) & 0xFF) >> 6) << 4);
                         m = (((h.w >> sh) & 0xFF) >> 4) | ((((h.z >> sh) & 0xFF) >> 6) << 4);
                     }
+                    // low nibbles: masked in place; high nibbles: left in place as unsigned bytes 16 q — their dot with
+                    // the signed activation bytes is 16 x the sub-block's dot, exactly (one mask per word, no shift)
                     uint32_t q[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) q[i] = (hf ? (w[i] >> 4) : w[i]) & 0x0F0F0F0Fu;
+                    for (int i = 0; i < 8; ++i) q[i] = w[i] & (hf ? 0xF0F0F0F0u : 0x0F0F0F0Fu);
                     const float dsc = __fmul_rn(d, static_cast<float>(sc)), dm = __fmul_rn(dmin, static_cast<float>(m));
 #pragma unroll
                     for (int tt = 0; tt < TT; ++tt) {
                         if (tt >= nt) break;
-                        const uint32_t* xt = xs + tt * xwords;                      // the same addresses in every thread: broadcast
-                        const uint32_t x0 = xt[sb * 8 + j];
-                        const uint4 xa = *reinterpret_cast<const uint4*>(xt + nblk + 8 * (sb * 8 + j));
-                        const uint4 xb = *reinterpret_cast<const uint4*>(xt + nblk + 8 * (sb * 8 + j) + 4);
+                        const uint32_t* xt = xs + tt * xsw;                         // the same addresses in every thread: broadcast
+                        const float2 xds = *reinterpret_cast<const float2*>(xt + 2 * (sb * 8 + j));
+                        const uint4 xa = *reinterpret_cast<const uint4*>(xt + 2 * nblk + 8 * (sb * 8 + j));
+                        const uint4 xb = *reinterpret_cast<const uint4*>(xt + 2 * nblk + 8 * (sb * 8 + j) + 4);
                         const uint32_t xq[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                         int dot = 0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dot = dp4(q[i], xq[i], dot);
-                        const float t1 = __fmul_rn(__fmul_rn(dsc, hlo(x0)), static_cast<float>(dot));
-                        const float t2 = __fmul_rn(dm, hhi(x0));
+                        for (int i = 0; i < 8; ++i) dot = hf ? dp4_us(q[i], xq[i], dot) : dp4(q[i], xq[i], dot);
+                        if (hf) dot >>= 4;
+                        const float t1 = __fmul_rn(__fmul_rn(dsc, xds.x), static_cast<float>(dot));
+                        const float t2 = __fmul_rn(dm, xds.y);
                         c[tt] = acc16h(c[tt], __fsub_rn(t1, t2));
                     }
                 }
@@ -408,14 +437,16 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_mma_q4k_kernel(const uint8_t*
 
     // copy plan of a stage, the same in every stage: 9 weight pieces per thread (as in the tile kernel) and the
     // 8 tokens x 18 activation pieces over the first 144 piece slots (tokens past the end re-read the last token)
-    const uint8_t* src[9];
-    uint32_t dsto[9];
+    const uint8_t* src[9];   // advanced by one super-block per issued stage
+    uint32_t dsto[9];        // shared-space address of the piece in the buffer of the next stage
+    const uint32_t ws_s = static_cast<uint32_t>(__cvta_generic_to_shared(ws));
+    const uint32_t xs_s = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
         const int p = tid + RT_ROWS * j, r = p / 9, c = p - 9 * r;
         const int64_t row = min(row0 + r, O - 1);
         src[j] = W + row * rowB + c * 16;
-        dsto[j] = static_cast<uint32_t>(r * RT_PITCH + c * 16);
+        dsto[j] = ws_s + static_cast<uint32_t>(r * RT_PITCH + c * 16);
     }
     const uint8_t* xsrc[2];
     uint32_t xdst[2];
@@ -423,15 +454,25 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_mma_q4k_kernel(const uint8_t*
     for (int j = 0; j < 2; ++j) {
         const int p = min(tid + RT_ROWS * j, RM_TOK * 18 - 1), tk = p / 18, c = p - 18 * tk;
         xsrc[j] = XQ + (t0 + min(tk, nt - 1)) * xrowB + c * 16;
-        xdst[j] = static_cast<uint32_t>(tk * (RM_XPITCH * 4) + c * 16);
+        xdst[j] = xs_s + static_cast<uint32_t>(tk * (RM_XPITCH * 4) + c * 16);
     }
-    auto issue = [&](int st) {   // super-block st -> buffer st & 1
-        uint8_t* dst = ws + static_cast<size_t>(st & 1) * RT_ROWS * RT_PITCH;
-        uint8_t* xd = xs + static_cast<size_t>(st & 1) * RM_TOK * RM_XPITCH * 4;
+    int bstep = RT_ROWS * RT_PITCH, xstep = RM_TOK * RM_XPITCH * 4;   // to the other buffer
+    auto issue = [&](int) {   // the next stage (super-block st) -> buffer st & 1; called once per stage, in order
 #pragma unroll
-        for (int j = 0; j < 9; ++j) cp_async16(dst + dsto[j], src[j] + static_cast<int64_t>(st) * 144);
-        cp_async16(xd + xdst[0], xsrc[0] + static_cast<int64_t>(st) * 288);
-        if (tid < RM_TOK * 18 - RT_ROWS) cp_async16(xd + xdst[1], xsrc[1] + static_cast<int64_t>(st) * 288);
+        for (int j = 0; j < 9; ++j) {
+            cp_async16_s(dsto[j], src[j]);
+            src[j] += 144;
+            dsto[j] += bstep;
+        }
+        cp_async16_s(xdst[0], xsrc[0]);
+        if (tid < RM_TOK * 18 - RT_ROWS) cp_async16_s(xdst[1], xsrc[1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            xsrc[j] += 288;
+            xdst[j] += xstep;
+        }
+        bstep = -bstep;
+        xstep = -xstep;
         cp_async_commit();
     };
     issue(0);
@@ -536,7 +577,7 @@ static bool launch_tile_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64
     // one token at K = 4096: 50 KB, four CTAs per SM);
     // a layer with more tokens than the tile streams its weights once per token tile
     constexpr size_t LIMIT = 113 * 1024;
-    auto smem_of = [&](int t) { return ((static_cast<size_t>(t) * (K / 32) * 36 + 15) & ~size_t{15}) + 2 * static_cast<size_t>(RT_ROWS) * RT_PITCH; };
+    auto smem_of = [&](int t) { return static_cast<size_t>(t) * (K / 32) * 40 + 2 * static_cast<size_t>(RT_ROWS) * RT_PITCH; };
     int tt = T == 1 ? 1 : T <= 4 ? 4 : 8;
     while (tt > 1 && smem_of(tt) > LIMIT) tt = tt == 8 ? 4 : 1;
     const size_t smem = smem_of(tt);
