@@ -256,12 +256,16 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
 // ---- Q4_K, tiled: HBM-rate form of the same arithmetic ---------------------------------------------------------------
 // One thread per weight row still (the accumulation chain of an output is sequential), but the packed rows reach the
 // threads through shared memory: the CTA's 128 threads copy a tile of 128 rows x 1 super-block (144 B per row) with
-// coalesced 16-byte cp.async into a double-buffered stage (176-byte row pitch: the threads' 128-bit reads of their own
-// row are conflict free; small stages keep four CTAs = 16 warps per SM for the single-token case, whose per-row chain of
-// dependent operations needs the warps), and the Q8_1 activations of the CTA's token tile are staged once.  Loads of the next stage
+// coalesced 16-byte cp.async into a double-buffered stage (odd row pitch in 16-byte vectors: the threads' 128-bit reads of
+// their own row are conflict free; small stages keep five CTAs = 20 warps per SM for the single-token case, whose per-row
+// chain of dependent operations needs the warps), and the Q8_1 activations of the CTA's token tile are staged once.  Loads of the next stage
 // overlap the arithmetic of the current one, so the kernel streams the weights once at HBM rate instead of waiting on
 // every thread's own scattered 16-byte loads.
-constexpr int RT_ROWS = 128, RT_SB = 1, RT_PITCH = RT_SB * 144 + 32;   // 176 B = 11 vectors: an odd pitch, 45 KB for both stages
+// Row pitch of a stage (template parameter RT_PITCH): 144 B = the rows packed densely, 9 vectors = an odd pitch, so the
+// threads' 128-bit reads of their own rows are conflict free (vector slot (9 r + c) mod 8 = (r + c) mod 8) and so are the
+// 32-bit fragment loads of the tensor-core kernel (bank 36 g + tg = 4 g + tg mod 32); 36 KB for both stages, five CTAs
+// per SM.  176 B (11 vectors, four CTAs per SM) was the first version and stays selectable (GGQ_REFMODE_PITCH=176).
+constexpr int RT_ROWS = 128, RT_SB = 1;
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
                  : "memory");
@@ -276,7 +280,7 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst_shared, const void* sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int TT>
+template <int TT, int RT_PITCH>
 __global__ void __launch_bounds__(RT_ROWS) refmode_tile_q4k_kernel(const uint8_t* __restrict__ W, const uint8_t* __restrict__ XQ,
                                                                    __half* __restrict__ C, int64_t O, int64_t T, int64_t K) {
     extern __shared__ __align__(16) uint8_t rsm[];
@@ -422,6 +426,7 @@ __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, ui
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
+template <int RT_PITCH>
 __global__ void __launch_bounds__(RT_ROWS) refmode_mma_q4k_kernel(const uint8_t* __restrict__ W, const uint8_t* __restrict__ XQ,
                                                                   __half* __restrict__ C, int64_t O, int64_t T, int64_t K) {
     extern __shared__ __align__(16) uint8_t rsm[];
@@ -556,18 +561,28 @@ __global__ void __launch_bounds__(RT_ROWS) refmode_mma_q4k_kernel(const uint8_t*
         }
 }
 
+static int refmode_pitch() {   // dev: GGQ_REFMODE_PITCH=176 selects the first version's padded row pitch
+    static const int pitch = getenv("GGQ_REFMODE_PITCH") && atoi(getenv("GGQ_REFMODE_PITCH")) == 176 ? 176 : 144;
+    return pitch;
+}
+
 static bool launch_mma_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64_t O, int64_t T, int64_t K, cudaStream_t s) {
-    constexpr int SMEM = 2 * RT_ROWS * RT_PITCH + 2 * RM_TOK * RM_XPITCH * 4;   // 51456 B: four CTAs per SM
+    const int pitch = refmode_pitch();
+    const int smem = 2 * RT_ROWS * pitch + 2 * RM_TOK * RM_XPITCH * 4;   // 43264 B: five CTAs per SM (176: 51456 B, four)
     const int64_t gx = (O + RT_ROWS - 1) / RT_ROWS, gy = (T + RM_TOK - 1) / RM_TOK;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || gx > 0x7fffffff || gy > 65535) return false;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(refmode_mma_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        configured[dev] = true;
-    }
-    refmode_mma_q4k_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), RT_ROWS, SMEM, s>>>(w, x, c, O, T, K);
+    auto go = [&](auto kern) {
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            configured[dev] = true;
+        }
+        kern<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), RT_ROWS, smem, s>>>(w, x, c, O, T, K);
+    };
+    if (pitch == 144) go(refmode_mma_q4k_kernel<144>);
+    else go(refmode_mma_q4k_kernel<176>);
     return true;
 }
 
@@ -577,7 +592,8 @@ static bool launch_tile_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64
     // one token at K = 4096: 50 KB, four CTAs per SM);
     // a layer with more tokens than the tile streams its weights once per token tile
     constexpr size_t LIMIT = 113 * 1024;
-    auto smem_of = [&](int t) { return static_cast<size_t>(t) * (K / 32) * 40 + 2 * static_cast<size_t>(RT_ROWS) * RT_PITCH; };
+    const int pitch = refmode_pitch();
+    auto smem_of = [&](int t) { return static_cast<size_t>(t) * (K / 32) * 40 + 2 * static_cast<size_t>(RT_ROWS) * pitch; };
     int tt = T == 1 ? 1 : T <= 4 ? 4 : 8;
     while (tt > 1 && smem_of(tt) > LIMIT) tt = tt == 8 ? 4 : 1;
     const size_t smem = smem_of(tt);
@@ -594,9 +610,15 @@ static bool launch_tile_q4k(const uint8_t* w, const uint8_t* x, __half* c, int64
         }
         kern<<<grid, RT_ROWS, smem, s>>>(w, x, c, O, T, K);
     };
-    if (tt == 1) go(refmode_tile_q4k_kernel<1>);
-    else if (tt == 4) go(refmode_tile_q4k_kernel<4>);
-    else go(refmode_tile_q4k_kernel<8>);
+    if (pitch == 144) {
+        if (tt == 1) go(refmode_tile_q4k_kernel<1, 144>);
+        else if (tt == 4) go(refmode_tile_q4k_kernel<4, 144>);
+        else go(refmode_tile_q4k_kernel<8, 144>);
+    } else {
+        if (tt == 1) go(refmode_tile_q4k_kernel<1, 176>);
+        else if (tt == 4) go(refmode_tile_q4k_kernel<4, 176>);
+        else go(refmode_tile_q4k_kernel<8, 176>);
+    }
     return true;
 }
 
