@@ -214,7 +214,9 @@ int ggq_dequant_q6_k_f32(const void* W, void* out, int64_t O, int64_t K, void* s
  * kernels/cpu_impls/mmq_{q8_0,q4_k,q6_k}_q8_1_cpu.py, so C[T, O] equals their result bit for bit.  One thread per weight
  * row (the fp16 accumulation chain of an output is sequential in the reference), vector loads and DP4A block dots when
  * the rows are whole 32-bit words (Q4_K always — through a cp.async-filled shared-memory tile; Q8_0 / Q6_K: an even
- * number of blocks per row), byte-wise otherwise.
+ * number of blocks per row), byte-wise otherwise.  Q4_K with T >= 3 and XQ 16-byte aligned: the block dots of 16 rows x
+ * 8 tokens by one integer tensor-core MMA, the chains in the accumulator-fragment layout (same bits).  Kernel selection
+ * depends only on shape and pointer alignment (W 16-byte aligned and XQ 4-byte aligned for the vector kernels).
  * For callers that want the reference's own numbers: its int8 activation noise (~5e-3) is outside the tolerance the
  * fp16-activation entry points above are held to.
  */
