@@ -258,18 +258,14 @@ __global__ void __launch_bounds__(128) refmode_fast_kernel(const uint8_t* __rest
 // threads through shared memory: the CTA's 128 threads copy a tile of 128 rows x 1 super-block (144 B per row) with
 // coalesced 16-byte cp.async into a double-buffered stage (odd row pitch in 16-byte vectors: the threads' 128-bit reads of
 // their own row are conflict free; small stages keep five CTAs = 20 warps per SM for the single-token case, whose per-row
-// chain of dependent operations needs the warps), and the Q8_1 activations of the CTA's token tile are staged once.  Loads of the next stage
-// overlap the arithmetic of the current one, so the kernel streams the weights once at HBM rate instead of waiting on
-// every thread's own scattered 16-byte loads.
+// chain of dependent operations needs the warps), and the Q8_1 activations of the CTA's token tile are staged once.
+// Loads of the next stage overlap the arithmetic of the current one, so the kernel streams the weights once at HBM rate
+// instead of waiting on every thread's own scattered 16-byte loads.
 // Row pitch of a stage (template parameter RT_PITCH): 144 B = the rows packed densely, 9 vectors = an odd pitch, so the
 // threads' 128-bit reads of their own rows are conflict free (vector slot (9 r + c) mod 8 = (r + c) mod 8) and so are the
 // 32-bit fragment loads of the tensor-core kernel (bank 36 g + tg = 4 g + tg mod 32); 36 KB for both stages, five CTAs
 // per SM.  176 B (11 vectors, four CTAs per SM) was the first version and stays selectable (GGQ_REFMODE_PITCH=176).
 constexpr int RT_ROWS = 128, RT_SB = 1;
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
-                 : "memory");
-}
 __device__ __forceinline__ void cp_async16_s(uint32_t dst_shared, const void* src) {   // destination as a shared-space address
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }

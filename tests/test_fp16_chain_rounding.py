@@ -13,11 +13,13 @@ def _pairs():
     # structured cases: near-ties (b a fraction of a's ulp), subnormals, the largest finite values, cancellations
     base = rng.integers(0, 1 << 16, size=200_000, dtype=np.uint16).view(np.float16)
     shift = rng.integers(1, 14, size=base.size)
-    tiny = (np.abs(base.astype(np.float64)) * 2.0 ** -(10 + shift) * rng.choice([1.0, 1.5, 0.5, 0.75], size=base.size)).astype(np.float16)
+    with np.errstate(invalid="ignore", over="ignore"):
+        tiny = (np.abs(base.astype(np.float64)) * 2.0 ** -(10 + shift) * rng.choice([1.0, 1.5, 0.5, 0.75], size=base.size)).astype(np.float16)
     edge = np.array([0x0001, 0x0002, 0x03FF, 0x0400, 0x7BFF, 0x7BFE, 0x3C00, 0x3C01, 0x8001, 0xFBFF, 0x0000, 0x8000], dtype=np.uint16).view(np.float16)
     ea, eb = np.meshgrid(edge, edge)
-    a = np.concatenate([a, base, base, ea.ravel()])
-    b = np.concatenate([b, tiny, -base + tiny, eb.ravel()])
+    with np.errstate(invalid="ignore", over="ignore"):
+        a = np.concatenate([a, base, base, ea.ravel()])
+        b = np.concatenate([b, tiny, -base + tiny, eb.ravel()])
     ok = np.isfinite(a) & np.isfinite(b)
     return a[ok], b[ok]
 
