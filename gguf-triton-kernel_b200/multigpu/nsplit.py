@@ -203,6 +203,10 @@ class NSplitLinear:
                 self._launch_sync(T)
 
         def replay():
+            if self._after_gemm:
+                # same rule as forward(): a T > 16 GEMM step wrote buffer 0 outside the even/odd discipline
+                self._symm.barrier(channel=0)
+                self._after_gemm = False
             g.replay()
             self._epoch += n
         return replay
