@@ -203,3 +203,22 @@ def test_describe_and_push_columns_host_side():
     assert L.ggq_push_columns(None, dst, 2, 64, 32, 4, None) == -2
     bad = (P * 2)(256, None)
     assert L.ggq_push_columns(one, bad, 2, 64, 32, 4, None) == -2
+
+
+def test_reference_arithmetic_mode_argument_errors_and_no_cpu_path():
+    """ggq_mm_ref_q8_1 validates format / shape / pointers on the host; the Python mirror of kernels/cpu_impls refuses CPU
+    tensors instead of falling back."""
+    from kernels import _ext, q8_1_mode
+    L = _ext.lib()
+    L.ggq_mm_ref_q8_1.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int64] * 3 + [ctypes.c_void_p]
+    L.ggq_mm_ref_q8_1.restype = ctypes.c_int
+    one = ctypes.c_void_p(256)
+    assert L.ggq_mm_ref_q8_1(7, one, one, one, 4, 1, 256, None) == -4      # unknown format
+    assert L.ggq_mm_ref_q8_1(1, one, one, one, 4, 1, 128, None) == -1      # K % 256
+    assert L.ggq_mm_ref_q8_1(0, one, one, one, 4, 1, 33, None) == -1       # K % 32
+    assert L.ggq_mm_ref_q8_1(1, None, one, one, 4, 1, 256, None) == -2     # NULL weights
+    assert L.ggq_mm_ref_q8_1(1, None, None, None, 0, 1, 256, None) == 0    # empty problem
+    A = torch.zeros(4 * 144, dtype=torch.int8)
+    B = torch.zeros(36 * 8, dtype=torch.int8)
+    with pytest.raises(ValueError, match="no CPU path"):
+        q8_1_mode.mmq_q4_k_q8_1(A, B, 4, 1, 256)
